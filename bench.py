@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the wave-generation hot path (spectrum propagation -> 4 packed N x N
+inverse FFTs -> displacement/normal/foam maps) on B200, per the driver contract.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                      (CPU arm: the oracle on the host cores)
+
+One "step" = one batched update of every cascade resident on a GPU (default workload: BASELINE.json
+configs[1], 256x256 x 4 cascades, batched as --sets independent 4-cascade sets per GPU so that the
+working set, 40 B/texel algorithmic + 64 B/texel scratch, exceeds the 126 MB L2).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_TEXEL = 40.0       # read h0 16 + read foam texel 8 + write 2 x RGBA16F 16
+METRIC = "ifft_cascades_per_sec"
+UNIT = "cascades/s"
+
+DEMO_SETS = [   # main.tscn:43-83 + wave_cascade_parameters.gd defaults
+    dict(tile_length=(88.0, 88.0), displacement_scale=1.0, normal_scale=1.0, wind_speed=10.0, wind_direction=20.0,
+         fetch_length=150.0, swell=0.8, spread=0.2, detail=1.0, whitecap=0.5, foam_amount=8.0),
+    dict(tile_length=(57.0, 57.0), displacement_scale=0.75, normal_scale=1.0, wind_speed=5.0, wind_direction=15.0,
+         fetch_length=150.0, swell=0.8, spread=0.4, detail=1.0, whitecap=0.5, foam_amount=0.0),
+    dict(tile_length=(16.0, 16.0), displacement_scale=0.0, normal_scale=0.25, wind_speed=20.0, wind_direction=20.0,
+         fetch_length=550.0, swell=0.8, spread=0.4, detail=1.0, whitecap=0.25, foam_amount=3.0),
+    dict(tile_length=(50.0, 50.0), displacement_scale=1.0, normal_scale=1.0, wind_speed=20.0, wind_direction=0.0,
+         fetch_length=550.0, swell=0.8, spread=0.2, detail=1.0, whitecap=0.5, foam_amount=5.0),
+]
+
+
+def synth_params(cls, global_index: int):
+    """Synthetic workload of SURVEY 8d: demo parameter sets cycled, fixed integer seeds, time0 = 120 + pi*c."""
+    kw = dict(DEMO_SETS[global_index % len(DEMO_SETS)])
+    kw.update(spectrum_seed=(1234 + 17 * global_index, -5678 + 31 * global_index),
+              time=120.0 + math.pi * (global_index % 8))
+    return cls(**kw)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.002)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def cpu_arm(map_size: int, cascades: int, steps: int, warmup: int, budget_s=None):
+    """The reference's CPU implementation of the path = the C oracle (oracle/), all host threads.
+    Returns (cascades_per_sec, seconds_per_step, cores, sample description)."""
+    from oracle import pyoracle as po
+    po.set_modes(po.MATH_DET, po.CONTRACT_FMA)
+    cores = po.lib().oracle_num_threads()
+    params = [synth_params(po.CascadeParams, c) for c in range(cascades)]
+    gen = po.OracleWaveGenerator(map_size)
+    gen.keep_f32 = False
+    for _ in range(max(1, warmup)):          # first step also generates the spectra (not steady state)
+        gen.update_all(1.0 / 50.0, params)
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps:
+        gen.update_all(1.0 / 50.0, params)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 >= budget_s:
+            break
+    dt = time.perf_counter() - t0
+    steps = done
+    sample = f"{steps} steady-state updates of {cascades} cascades at {map_size}x{map_size} (oracle, DETMATH+FMA, OpenMP)"
+    return cascades * steps / dt, dt / steps, cores, sample
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    # bounded sample of the same workload: one 4-cascade set per step
+    cps, sps, cores, sample = cpu_arm(args.map_size, args.cascades_per_set, args.steps, min(args.warmup, 2))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.map_size}x{args.map_size} x {args.cascades_per_set} cascades, full pipeline incl. foam",
+                   "map_size": args.map_size, "cascades_per_step": args.cascades_per_set,
+                   "note": "reference (Godot GLSL on lavapipe) is not runnable in this image; CPU arm = C oracle port"},
+        "mtexels_per_sec": cps * args.map_size * args.map_size / 1e6,
+        "cpu_baseline": {"value": cps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": cps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--map-size", type=int, default=256)
+    ap.add_argument("--cascades-per-set", type=int, default=4)
+    ap.add_argument("--sets", type=int, default=32, help="independent cascade sets resident per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import godotoceanwaves_b200 as gow
+    from godotoceanwaves_b200 import build as native_build
+
+    native_build.build_native()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback for the native arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    N = args.map_size
+    C = args.sets * args.cascades_per_set                 # cascades resident on this GPU (weak scaling)
+    texels_per_step = C * N * N
+    gen = gow.WaveGenerator(device=local_rank)
+    gen.map_size = N
+    gen.init_gpu(C)
+    params = [synth_params(gow.WaveCascadeParameters, rank * C + c) for c in range(C)]
+    delta = 1.0 / 50.0
+
+    # ---- warm-up (first step also generates the spectra) ----
+    for _ in range(args.warmup):
+        gen.update_all(delta, params)
+    gen.synchronize()
+
+    # ---- device-timed region: inputs resident in HBM, CUDA events on the launching stream ----
+    sampler = ClockSampler(local_rank)
+    launches0 = gen.info().kernel_launches
+    barrier()
+    sampler.start()
+    gen.timer_start()
+    for _ in range(args.steps):
+        gen.update_all(delta, params)
+    ms = gen.timer_stop()
+    clocks = sampler.stop()
+    barrier()
+    launches = gen.info().kernel_launches - launches0
+    ms = max_over_ranks(ms)
+    value = world * C * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel times (CUDA events between the two kernels), averaged over a few steps ----
+    gen.set_profiling(True)
+    ka = kb = 0.0
+    reps = min(args.steps, 20)
+    for _ in range(reps):
+        gen.update_all(delta, params)
+        _, a, b = gen.last_kernel_times()
+        ka += a
+        kb += b
+    gen.set_profiling(False)
+    ka, kb = ka / reps, kb / reps
+
+    # ---- end to end through the public API with host buffers: params H2D + both maps D2H every step ----
+    lib = gow.load_library()
+    import ctypes as Ct
+    map_bytes = C * N * N * 8
+    hd, hn = Ct.c_void_p(), Ct.c_void_p()
+    gow.native.check(lib.ocean_host_alloc(Ct.byref(hd), map_bytes))
+    gow.native.check(lib.ocean_host_alloc(Ct.byref(hn), map_bytes))
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        gen.update_all(delta, params)
+        gow.native.check(lib.ocean_copy_maps_to_host(gen.context, 0, C, hd, hn))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        gen.update_all(delta, params)                                          # marshals + uploads dispatch records
+        gow.native.check(lib.ocean_copy_maps_to_host_async(gen.context, 0, C, hd, hn))
+        gen.synchronize()                                                      # result is on the host
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * C * e2e_steps / e2e_s
+    h2d_bytes = C * 32                                                         # one CascadeDispatch record per cascade
+    d2h_bytes = 2 * map_bytes
+    probe = np.frombuffer((Ct.c_uint16 * 4).from_address(hd.value), np.float16)
+    assert np.all(np.isfinite(probe.astype(np.float32)))
+    gow.native.check(lib.ocean_host_free(hd))
+    gow.native.check(lib.ocean_host_free(hn))
+    gen.free()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak_gbs, peak_src = measured_peaks()
+    step_s = ms * 1e-3 / args.steps
+    achieved = ALGO_BYTES_PER_TEXEL * texels_per_step / step_s / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{N}x{N} x {args.cascades_per_set} cascades, full pipeline incl. foam, {args.sets} independent sets per GPU per step",
+                   "map_size": N, "cascades_per_set": args.cascades_per_set, "sets_per_gpu": args.sets,
+                   "cascades_per_step_per_gpu": C, "parallelism": f"cascade-sharded x{world}, no data-path collective",
+                   "l2": f"working set {(ALGO_BYTES_PER_TEXEL + 64) * texels_per_step / 2**20:.0f} MiB per step > 126 MB L2 (inputs larger than L2)"},
+        "mtexels_per_sec": value * N * N / 1e6,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel": "k_modulate_rowfft + k_colfft_unpack (one step = the launch pair)",
+                     "algorithmic_bytes_per_step": ALGO_BYTES_PER_TEXEL * texels_per_step,
+                     "kernel_ms": {"k_modulate_rowfft": ka, "k_colfft_unpack": kb}},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": e2e_s * 1e3 / e2e_steps, "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cps, sps, cores, sample = cpu_arm(N, args.cascades_per_set, 100000, 1, budget_s=args.cpu_seconds)
+        line["cpu_baseline"] = {"value": cps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

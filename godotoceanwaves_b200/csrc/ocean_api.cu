@@ -1,0 +1,555 @@
+// ocean_api.cu -- the C ABI of libocean.so (include/ocean.h) and the host-side sequencing of
+// the reference's WaveGenerator (assets/water/wave_generator.gd:17-121): resource allocation,
+// dirty-flag handling, push-constant rounding (assets/render_context.gd:122-135), the
+// update / _process pending-cascade state machine, and the hand-off of the finished maps.
+// No CPU fallback exists: every compute entry point launches the sm_100a kernels or fails.
+#include "../../include/ocean.h"
+#include "ocean_kernels.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define OCEAN_CUDA(expr)                                                                       \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(OCEAN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr double kG = 9.81;       // wave_generator.gd:5
+constexpr double kDepth = 20.0;   // wave_generator.gd:6
+constexpr int kRing = 8;          // pinned staging slots for dispatch records
+
+}  // namespace
+
+struct ocean_generator {
+    int device = 0;
+    int map_size = 0;
+    int num_cascades = 0;
+    cudaStream_t stream = nullptr;
+    ocean::DeviceBuffers buf{};
+    float2* twiddles = nullptr;
+    float2* export_buf = nullptr;                       // rowpass export scratch (lazy)
+    ocean::CascadeDispatch* d_cascade = nullptr;        // [num_cascades]
+    ocean::SpectrumDispatch* d_spectrum = nullptr;      // [num_cascades]
+    ocean::CascadeDispatch* h_cascade = nullptr;        // pinned [kRing][num_cascades]
+    ocean::SpectrumDispatch* h_spectrum = nullptr;      // pinned [kRing][num_cascades]
+    cudaEvent_t ring_done[kRing] = {};
+    int ring_next = 0;
+    cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
+    cudaEvent_t prof[4] = {};                           // gen-start, A-start, A/B boundary, B-end
+    bool profiling = false;
+    bool prof_valid = false, prof_had_gen = false;
+    std::vector<ocean_cascade_params> pass_parameters;  // wave_generator.gd:14
+    int pass_num_cascades_remaining = 0;                // wave_generator.gd:15
+    uint64_t kernel_launches = 0;
+    uint64_t cascade_updates = 0;
+    uint64_t device_bytes = 0;
+};
+
+namespace {
+
+int check_gen(ocean_generator* g) {
+    if (!g) return fail(OCEAN_ERR_INVALID_ARGUMENT, "generator handle is NULL");
+    cudaError_t e = cudaSetDevice(g->device);
+    if (e != cudaSuccess) return fail(OCEAN_ERR_CUDA, "cudaSetDevice(%d) failed: %s", g->device, cudaGetErrorString(e));
+    return OCEAN_OK;
+}
+
+template <typename T>
+cudaError_t dev_alloc(ocean_generator* g, T** p, size_t count) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+    if (e == cudaSuccess) g->device_bytes += count * sizeof(T);
+    return e;
+}
+
+void release(ocean_generator* g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    if (g->stream) cudaStreamSynchronize(g->stream);
+    cudaFree(g->buf.spectrum);
+    cudaFree(g->buf.rowpass);
+    cudaFree(g->buf.displacement);
+    cudaFree(g->buf.normal);
+    cudaFree(g->buf.displacement_f32);
+    cudaFree(g->buf.normal_f32);
+    cudaFree(g->twiddles);
+    cudaFree(g->export_buf);
+    cudaFree(g->d_cascade);
+    cudaFree(g->d_spectrum);
+    if (g->h_cascade) cudaFreeHost(g->h_cascade);
+    if (g->h_spectrum) cudaFreeHost(g->h_spectrum);
+    for (auto& ev : g->ring_done)
+        if (ev) cudaEventDestroy(ev);
+    if (g->timer_start) cudaEventDestroy(g->timer_start);
+    if (g->timer_stop) cudaEventDestroy(g->timer_stop);
+    for (auto& ev : g->prof)
+        if (ev) cudaEventDestroy(ev);
+    if (g->stream) cudaStreamDestroy(g->stream);
+    delete g;
+}
+
+// Push constants of wave_generator.gd:69-71 (spectrum_compute) with the binary64 -> binary32
+// rounding of render_context.gd:134.
+ocean::SpectrumDispatch make_spectrum_dispatch(const ocean_cascade_params& p, int cascade) {
+    ocean::SpectrumDispatch d;
+    const double alpha = ocean_jonswap_alpha(p.wind_speed, p.fetch_length * 1e3);
+    const double omega = ocean_jonswap_peak_angular_frequency(p.wind_speed, p.fetch_length * 1e3);
+    d.cascade = cascade;
+    d.seed_x = p.spectrum_seed[0];
+    d.seed_y = p.spectrum_seed[1];
+    d.tile_x = p.tile_length[0];
+    d.tile_y = p.tile_length[1];
+    d.alpha = (float)alpha;
+    d.peak_frequency = (float)omega;
+    d.wind_speed = (float)p.wind_speed;
+    d.angle = (float)(p.wind_direction * (M_PI / 180.0));   // deg_to_rad
+    d.depth = (float)kDepth;
+    d.swell = (float)p.swell;
+    d.detail = (float)p.detail;
+    d.spread = (float)p.spread;
+    return d;
+}
+
+// Push constants of wave_generator.gd:73 (spectrum_modulate) and :85 (fft_unpack).
+ocean::CascadeDispatch make_cascade_dispatch(const ocean_cascade_params& p, int cascade) {
+    ocean::CascadeDispatch d;
+    d.cascade = cascade;
+    d.tile_x = p.tile_length[0];
+    d.tile_y = p.tile_length[1];
+    d.depth = (float)kDepth;
+    d.time = (float)p.time;
+    d.whitecap = (float)p.whitecap;
+    d.foam_grow_rate = (float)p.foam_grow_rate;
+    d.foam_decay_rate = (float)p.foam_decay_rate;
+    return d;
+}
+
+// Runs WaveGenerator._update (wave_generator.gd:65-85) for the cascades listed in `indices`
+// (all of them in ONE batched launch sequence; cascades are independent).
+int run_cascades(ocean_generator* g, const int* indices, int n) {
+    if (n <= 0) return OCEAN_OK;
+    const int slot = g->ring_next;
+    g->ring_next = (g->ring_next + 1) % kRing;
+    OCEAN_CUDA(cudaEventSynchronize(g->ring_done[slot]));           // staging slot free again?
+    ocean::CascadeDispatch* hc = g->h_cascade + (size_t)slot * g->num_cascades;
+    ocean::SpectrumDispatch* hs = g->h_spectrum + (size_t)slot * g->num_cascades;
+    int n_dirty = 0;
+    for (int k = 0; k < n; ++k) {
+        const int i = indices[k];
+        ocean_cascade_params& p = g->pass_parameters[i];
+        if (p.should_generate_spectrum) {                            // :68-72
+            hs[n_dirty++] = make_spectrum_dispatch(p, i);
+            p.should_generate_spectrum = 0;
+        }
+        hc[k] = make_cascade_dispatch(p, i);                         // :73,85
+    }
+    if (g->profiling) OCEAN_CUDA(cudaEventRecord(g->prof[0], g->stream));
+    if (n_dirty) {
+        OCEAN_CUDA(cudaMemcpyAsync(g->d_spectrum, hs, sizeof(ocean::SpectrumDispatch) * n_dirty, cudaMemcpyHostToDevice, g->stream));
+        OCEAN_CUDA(ocean::launch_spectrum_compute(g->buf, g->d_spectrum, n_dirty, g->stream));
+        g->kernel_launches += 1;
+    }
+    OCEAN_CUDA(cudaMemcpyAsync(g->d_cascade, hc, sizeof(ocean::CascadeDispatch) * n, cudaMemcpyHostToDevice, g->stream));
+    OCEAN_CUDA(cudaEventRecord(g->ring_done[slot], g->stream));
+    int launched = 0;
+    if (g->profiling) OCEAN_CUDA(cudaEventRecord(g->prof[1], g->stream));
+    OCEAN_CUDA(ocean::launch_cascade_update(g->buf, g->d_cascade, n, g->stream, &launched, g->profiling ? g->prof[2] : nullptr));
+    if (g->profiling) {
+        OCEAN_CUDA(cudaEventRecord(g->prof[3], g->stream));
+        g->prof_valid = true;
+        g->prof_had_gen = n_dirty != 0;
+    }
+    g->kernel_launches += (uint64_t)launched;
+    g->cascade_updates += (uint64_t)n;
+    return OCEAN_OK;
+}
+
+int validate_params(ocean_generator* g, const ocean_cascade_params* parameters, int count) {
+    if (!parameters) return fail(OCEAN_ERR_INVALID_ARGUMENT, "parameters is NULL");
+    if (count <= 0) return fail(OCEAN_ERR_INVALID_ARGUMENT, "parameters.size() must be != 0 (wave_generator.gd:91)");
+    if (count > g->num_cascades)
+        return fail(OCEAN_ERR_INVALID_ARGUMENT, "%d cascades passed but the generator was created with %d layers", count, g->num_cascades);
+    for (int i = 0; i < count; ++i) {
+        const ocean_cascade_params& p = parameters[i];
+        if (!(p.tile_length[0] > 0.0f) || !(p.tile_length[1] > 0.0f))
+            return fail(OCEAN_ERR_INVALID_ARGUMENT, "cascade %d: tile_length must be positive", i);
+        if (!(p.wind_speed > 0.0) || !(p.fetch_length > 0.0))
+            return fail(OCEAN_ERR_INVALID_ARGUMENT, "cascade %d: wind_speed and fetch_length must be positive (setters clamp to 1e-4)", i);
+    }
+    return OCEAN_OK;
+}
+
+int check_cascade(ocean_generator* g, int cascade) {
+    if (cascade < 0 || cascade >= g->num_cascades)
+        return fail(OCEAN_ERR_INVALID_ARGUMENT, "cascade index %d out of range [0,%d)", cascade, g->num_cascades);
+    return OCEAN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ocean_last_error(void) { return g_last_error.c_str(); }
+const char* ocean_version(void) { return "godotoceanwaves_b200 0.1 (sm_100a)"; }
+
+double ocean_jonswap_alpha(double wind_speed, double fetch_length) {             // wave_generator.gd:116-117
+    return 0.076 * std::pow(wind_speed * wind_speed / (fetch_length * kG), 0.22);
+}
+double ocean_jonswap_peak_angular_frequency(double wind_speed, double fetch_length) {   // wave_generator.gd:120-121
+    return 22.0 * std::pow(kG * kG / (wind_speed * fetch_length), 1.0 / 3.0);
+}
+
+int ocean_default_cascade_params(ocean_cascade_params* out) {                    // wave_cascade_parameters.gd:7-42
+    if (!out) return fail(OCEAN_ERR_INVALID_ARGUMENT, "out is NULL");
+    std::memset(out, 0, sizeof *out);
+    out->tile_length[0] = out->tile_length[1] = 50.0f;
+    out->displacement_scale = 1.0;
+    out->normal_scale = 1.0;
+    out->wind_speed = 20.0;
+    out->wind_direction = 0.0;
+    out->fetch_length = 550.0;
+    out->swell = 0.8;
+    out->spread = 0.2;
+    out->detail = 1.0;
+    out->whitecap = 0.5;
+    out->foam_amount = 5.0;
+    out->should_generate_spectrum = 1;
+    return OCEAN_OK;
+}
+
+int ocean_create(int device, int map_size, int num_cascades, ocean_generator** out) {
+    if (!out) return fail(OCEAN_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (map_size != 128 && map_size != 256 && map_size != 512 && map_size != 1024)
+        return fail(OCEAN_ERR_INVALID_ARGUMENT, "map_size %d not in {128,256,512,1024} (water.gd:38)", map_size);
+    if (num_cascades < 1) return fail(OCEAN_ERR_INVALID_ARGUMENT, "num_layers >= 1 required (render_context.gd:77)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(OCEAN_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(OCEAN_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device, ndev);
+    OCEAN_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    OCEAN_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(OCEAN_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+
+    ocean_generator* g = new (std::nothrow) ocean_generator();
+    if (!g) return fail(OCEAN_ERR_STATE, "out of host memory");
+    g->device = device;
+    g->map_size = map_size;
+    g->num_cascades = num_cascades;
+    const size_t NN = (size_t)map_size * map_size;
+    const size_t C = (size_t)num_cascades;
+#define CREATE_CUDA(expr)                                                                                        \
+    do {                                                                                                         \
+        cudaError_t e__ = (expr);                                                                                \
+        if (e__ != cudaSuccess) {                                                                                \
+            release(g);                                                                                          \
+            return fail(OCEAN_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));                        \
+        }                                                                                                        \
+    } while (0)
+    CREATE_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    CREATE_CUDA(dev_alloc(g, &g->buf.spectrum, C * NN));                  // wave_generator.gd:31
+    CREATE_CUDA(dev_alloc(g, &g->buf.rowpass, C * 2 * NN));               // replaces fft_buffer, :33
+    CREATE_CUDA(dev_alloc(g, &g->buf.displacement, C * NN));              // :34
+    CREATE_CUDA(dev_alloc(g, &g->buf.normal, C * NN));                    // :35
+    CREATE_CUDA(dev_alloc(g, &g->twiddles, (size_t)ocean::kTwiddleCount + 1));   // :32
+    CREATE_CUDA(dev_alloc(g, &g->d_cascade, C));
+    CREATE_CUDA(dev_alloc(g, &g->d_spectrum, C));
+    CREATE_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g->h_cascade), sizeof(ocean::CascadeDispatch) * kRing * C, cudaHostAllocDefault));
+    CREATE_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g->h_spectrum), sizeof(ocean::SpectrumDispatch) * kRing * C, cudaHostAllocDefault));
+    for (auto& ev : g->ring_done) CREATE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreate(&g->timer_start));
+    CREATE_CUDA(cudaEventCreate(&g->timer_stop));
+    for (auto& ev : g->prof) CREATE_CUDA(cudaEventCreate(&ev));
+    // textures start cleared (foam state = 0)
+    CREATE_CUDA(cudaMemsetAsync(g->buf.spectrum, 0, sizeof(float4) * C * NN, g->stream));
+    CREATE_CUDA(cudaMemsetAsync(g->buf.rowpass, 0, sizeof(float4) * C * 2 * NN, g->stream));
+    CREATE_CUDA(cudaMemsetAsync(g->buf.displacement, 0, sizeof(uint2) * C * NN, g->stream));
+    CREATE_CUDA(cudaMemsetAsync(g->buf.normal, 0, sizeof(uint2) * C * NN, g->stream));
+    g->buf.map_size = map_size;
+    g->buf.num_cascades = num_cascades;
+    g->buf.twiddles = g->twiddles;
+    CREATE_CUDA(ocean::configure_kernels(map_size));
+    CREATE_CUDA(ocean::init_twiddles(g->twiddles, g->stream));            // fft_butterfly once, :52-54
+    g->kernel_launches += 1;
+    CREATE_CUDA(cudaStreamSynchronize(g->stream));
+#undef CREATE_CUDA
+    *out = g;
+    return OCEAN_OK;
+}
+
+int ocean_destroy(ocean_generator* gen) {
+    if (!gen) return fail(OCEAN_ERR_INVALID_ARGUMENT, "generator handle is NULL");
+    release(gen);
+    return OCEAN_OK;
+}
+
+int ocean_update(ocean_generator* gen, double delta, ocean_cascade_params* parameters, int count) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    rc = validate_params(gen, parameters, count);
+    if (rc) return rc;
+    // wave_generator.gd:94-98: finish the cascades of the previous pass that were never processed
+    if (gen->pass_num_cascades_remaining != 0) {
+        std::vector<int> idx(gen->pass_num_cascades_remaining);
+        for (int i = 0; i < gen->pass_num_cascades_remaining; ++i) idx[i] = i;
+        // the reference dereferences the live Resource objects: refresh from the caller's array where it overlaps
+        for (int i = 0; i < gen->pass_num_cascades_remaining && i < count; ++i) gen->pass_parameters[i] = parameters[i];
+        rc = run_cascades(gen, idx.data(), (int)idx.size());
+        if (rc) return rc;
+        for (int i = 0; i < gen->pass_num_cascades_remaining && i < count; ++i)
+            parameters[i].should_generate_spectrum = gen->pass_parameters[i].should_generate_spectrum;
+        gen->pass_num_cascades_remaining = 0;
+    }
+    // :100-106
+    for (int i = 0; i < count; ++i) {
+        ocean_cascade_params& p = parameters[i];
+        p.time += delta;
+        p.foam_grow_rate = delta * p.foam_amount * 7.5;
+        p.foam_decay_rate = delta * std::fmax(0.5, 10.0 - p.foam_amount) * 1.15;
+    }
+    gen->pass_parameters.assign(parameters, parameters + count);       // :108
+    gen->pass_num_cascades_remaining = count;                          // :109
+    return OCEAN_OK;
+}
+
+int ocean_process(ocean_generator* gen, ocean_cascade_params* parameters, int count) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    if (gen->pass_num_cascades_remaining == 0) return OCEAN_OK;        // :58
+    if (parameters) {
+        if (count != (int)gen->pass_parameters.size())
+            return fail(OCEAN_ERR_INVALID_ARGUMENT, "ocean_process: count %d differs from the armed pass (%d)", count, (int)gen->pass_parameters.size());
+        rc = validate_params(gen, parameters, count);
+        if (rc) return rc;
+    }
+    gen->pass_num_cascades_remaining -= 1;                             // :59
+    const int i = gen->pass_num_cascades_remaining;
+    if (parameters) gen->pass_parameters[i] = parameters[i];
+    rc = run_cascades(gen, &i, 1);                                     // :61-63
+    if (rc) return rc;
+    if (parameters) parameters[i].should_generate_spectrum = gen->pass_parameters[i].should_generate_spectrum;
+    return OCEAN_OK;
+}
+
+int ocean_update_all(ocean_generator* gen, double delta, ocean_cascade_params* parameters, int count) {
+    int rc = ocean_update(gen, delta, parameters, count);
+    if (rc) return rc;
+    std::vector<int> idx(count);
+    for (int i = 0; i < count; ++i) idx[i] = i;
+    rc = run_cascades(gen, idx.data(), count);
+    if (rc) return rc;
+    for (int i = 0; i < count; ++i) parameters[i].should_generate_spectrum = gen->pass_parameters[i].should_generate_spectrum;
+    gen->pass_num_cascades_remaining = 0;
+    return OCEAN_OK;
+}
+
+int ocean_get_maps(ocean_generator* gen, void** displacement_dev, void** normal_dev, size_t* layer_bytes) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    if (displacement_dev) *displacement_dev = gen->buf.displacement;
+    if (normal_dev) *normal_dev = gen->buf.normal;
+    if (layer_bytes) *layer_bytes = sizeof(uint2) * (size_t)gen->map_size * gen->map_size;
+    return OCEAN_OK;
+}
+
+int ocean_copy_maps_to_host_async(ocean_generator* gen, int first, int count, void* displacement_host, void* normal_host) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    if (first < 0 || count < 0 || first + count > gen->num_cascades)
+        return fail(OCEAN_ERR_INVALID_ARGUMENT, "layer range [%d,%d) outside [0,%d)", first, first + count, gen->num_cascades);
+    const size_t layer = (size_t)gen->map_size * gen->map_size;
+    if (displacement_host)
+        OCEAN_CUDA(cudaMemcpyAsync(displacement_host, gen->buf.displacement + first * layer, sizeof(uint2) * layer * count, cudaMemcpyDeviceToHost, gen->stream));
+    if (normal_host)
+        OCEAN_CUDA(cudaMemcpyAsync(normal_host, gen->buf.normal + first * layer, sizeof(uint2) * layer * count, cudaMemcpyDeviceToHost, gen->stream));
+    return OCEAN_OK;
+}
+
+int ocean_copy_maps_to_host(ocean_generator* gen, int first, int count, void* displacement_host, void* normal_host) {
+    int rc = ocean_copy_maps_to_host_async(gen, first, count, displacement_host, normal_host);
+    if (rc) return rc;
+    OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+    return OCEAN_OK;
+}
+
+int ocean_synchronize(ocean_generator* gen) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+    return OCEAN_OK;
+}
+
+int ocean_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(OCEAN_ERR_INVALID_ARGUMENT, "ptr is NULL");
+    OCEAN_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return OCEAN_OK;
+}
+int ocean_host_free(void* ptr) {
+    OCEAN_CUDA(cudaFreeHost(ptr));
+    return OCEAN_OK;
+}
+
+int ocean_copy_spectrum_to_host(ocean_generator* gen, int cascade, float* host) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    if ((rc = check_cascade(gen, cascade))) return rc;
+    if (!host) return fail(OCEAN_ERR_INVALID_ARGUMENT, "host is NULL");
+    const size_t layer = (size_t)gen->map_size * gen->map_size;
+    OCEAN_CUDA(cudaMemcpyAsync(host, gen->buf.spectrum + cascade * layer, sizeof(float4) * layer, cudaMemcpyDeviceToHost, gen->stream));
+    OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+    return OCEAN_OK;
+}
+
+int ocean_enable_f32_taps(ocean_generator* gen, int enable) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+    const size_t n = (size_t)gen->num_cascades * gen->map_size * gen->map_size;
+    if (enable && !gen->buf.displacement_f32) {
+        OCEAN_CUDA(dev_alloc(gen, &gen->buf.displacement_f32, n));
+        OCEAN_CUDA(dev_alloc(gen, &gen->buf.normal_f32, n));
+        OCEAN_CUDA(cudaMemset(gen->buf.displacement_f32, 0, sizeof(float4) * n));
+        OCEAN_CUDA(cudaMemset(gen->buf.normal_f32, 0, sizeof(float4) * n));
+    } else if (!enable && gen->buf.displacement_f32) {
+        cudaFree(gen->buf.displacement_f32);
+        cudaFree(gen->buf.normal_f32);
+        gen->buf.displacement_f32 = gen->buf.normal_f32 = nullptr;
+        gen->device_bytes -= 2 * sizeof(float4) * n;
+    }
+    return OCEAN_OK;
+}
+
+int ocean_copy_f32_maps_to_host(ocean_generator* gen, int cascade, float* displacement_host, float* normal_host) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    if ((rc = check_cascade(gen, cascade))) return rc;
+    if (!gen->buf.displacement_f32) return fail(OCEAN_ERR_STATE, "binary32 taps are disabled; call ocean_enable_f32_taps(gen, 1) first");
+    const size_t layer = (size_t)gen->map_size * gen->map_size;
+    if (displacement_host)
+        OCEAN_CUDA(cudaMemcpyAsync(displacement_host, gen->buf.displacement_f32 + cascade * layer, sizeof(float4) * layer, cudaMemcpyDeviceToHost, gen->stream));
+    if (normal_host)
+        OCEAN_CUDA(cudaMemcpyAsync(normal_host, gen->buf.normal_f32 + cascade * layer, sizeof(float4) * layer, cudaMemcpyDeviceToHost, gen->stream));
+    OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+    return OCEAN_OK;
+}
+
+int ocean_copy_rowpass_to_host(ocean_generator* gen, int cascade, float* host) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    if ((rc = check_cascade(gen, cascade))) return rc;
+    if (!host) return fail(OCEAN_ERR_INVALID_ARGUMENT, "host is NULL");
+    const size_t layer = (size_t)gen->map_size * gen->map_size;
+    if (!gen->export_buf) OCEAN_CUDA(dev_alloc(gen, &gen->export_buf, 4 * layer));
+    OCEAN_CUDA(ocean::launch_rowpass_export(gen->buf, cascade, gen->export_buf, gen->stream));
+    gen->kernel_launches += 1;
+    OCEAN_CUDA(cudaMemcpyAsync(host, gen->export_buf, sizeof(float2) * 4 * layer, cudaMemcpyDeviceToHost, gen->stream));
+    OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+    return OCEAN_OK;
+}
+
+int ocean_copy_twiddles_to_host(ocean_generator* gen, float* host) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    if (!host) return fail(OCEAN_ERR_INVALID_ARGUMENT, "host is NULL");
+    OCEAN_CUDA(cudaMemcpyAsync(host, gen->twiddles, sizeof(float2) * (gen->map_size - 1), cudaMemcpyDeviceToHost, gen->stream));
+    OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+    return OCEAN_OK;
+}
+
+int ocean_get_foam_state(ocean_generator* gen, int cascade, uint16_t* host) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    if ((rc = check_cascade(gen, cascade))) return rc;
+    if (!host) return fail(OCEAN_ERR_INVALID_ARGUMENT, "host is NULL");
+    const size_t layer = (size_t)gen->map_size * gen->map_size;
+    const uint16_t* src = reinterpret_cast<const uint16_t*>(gen->buf.normal + cascade * layer) + 3;
+    OCEAN_CUDA(cudaMemcpy2DAsync(host, sizeof(uint16_t), src, sizeof(uint2), sizeof(uint16_t), layer, cudaMemcpyDeviceToHost, gen->stream));
+    OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+    return OCEAN_OK;
+}
+
+int ocean_set_foam_state(ocean_generator* gen, int cascade, const uint16_t* host) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    if ((rc = check_cascade(gen, cascade))) return rc;
+    if (!host) return fail(OCEAN_ERR_INVALID_ARGUMENT, "host is NULL");
+    const size_t layer = (size_t)gen->map_size * gen->map_size;
+    uint16_t* dst = reinterpret_cast<uint16_t*>(gen->buf.normal + cascade * layer) + 3;
+    OCEAN_CUDA(cudaMemcpy2DAsync(dst, sizeof(uint2), host, sizeof(uint16_t), sizeof(uint16_t), layer, cudaMemcpyHostToDevice, gen->stream));
+    OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+    return OCEAN_OK;
+}
+
+int ocean_timer_start(ocean_generator* gen) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    OCEAN_CUDA(cudaEventRecord(gen->timer_start, gen->stream));
+    return OCEAN_OK;
+}
+
+int ocean_timer_stop(ocean_generator* gen, float* elapsed_ms) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    if (!elapsed_ms) return fail(OCEAN_ERR_INVALID_ARGUMENT, "elapsed_ms is NULL");
+    OCEAN_CUDA(cudaEventRecord(gen->timer_stop, gen->stream));
+    OCEAN_CUDA(cudaEventSynchronize(gen->timer_stop));
+    OCEAN_CUDA(cudaEventElapsedTime(elapsed_ms, gen->timer_start, gen->timer_stop));
+    return OCEAN_OK;
+}
+
+int ocean_set_profiling(ocean_generator* gen, int enable) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    gen->profiling = enable != 0;
+    gen->prof_valid = false;
+    return OCEAN_OK;
+}
+
+int ocean_get_last_kernel_times(ocean_generator* gen, float* spectrum_ms, float* rowpass_ms, float* colpass_ms) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    if (!gen->prof_valid) return fail(OCEAN_ERR_STATE, "no profiled launch yet; call ocean_set_profiling(gen, 1) and run an update");
+    OCEAN_CUDA(cudaEventSynchronize(gen->prof[3]));
+    float t = 0.f;
+    if (spectrum_ms) { OCEAN_CUDA(cudaEventElapsedTime(&t, gen->prof[0], gen->prof[1])); *spectrum_ms = gen->prof_had_gen ? t : 0.f; }
+    if (rowpass_ms) OCEAN_CUDA(cudaEventElapsedTime(rowpass_ms, gen->prof[1], gen->prof[2]));
+    if (colpass_ms) OCEAN_CUDA(cudaEventElapsedTime(colpass_ms, gen->prof[2], gen->prof[3]));
+    return OCEAN_OK;
+}
+
+int ocean_get_info(ocean_generator* gen, ocean_info* out) {
+    if (!gen || !out) return fail(OCEAN_ERR_INVALID_ARGUMENT, "NULL argument");
+    out->device = gen->device;
+    out->map_size = gen->map_size;
+    out->num_cascades = gen->num_cascades;
+    out->pending_cascades = gen->pass_num_cascades_remaining;
+    out->kernel_launches = gen->kernel_launches;
+    out->cascade_updates = gen->cascade_updates;
+    out->device_bytes = gen->device_bytes;
+    return OCEAN_OK;
+}
+
+}  // extern "C"

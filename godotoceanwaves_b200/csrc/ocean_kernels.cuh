@@ -1,0 +1,59 @@
+// ocean_kernels.cuh -- launch interface between the C-ABI layer (ocean_api.cu) and the
+// sm_100a kernels (ocean_kernels.cu).  Internal; the public surface is include/ocean.h.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ocean {
+
+constexpr int kMaxMapSize = 1024;
+constexpr int kTwiddleCount = kMaxMapSize - 1;   // stage s, index j (< 2^s) lives at (1<<s)-1+j
+
+// Push constants of spectrum_compute.glsl:18-30 for one dirty cascade (already binary32).
+struct SpectrumDispatch {
+    int32_t cascade;
+    int32_t seed_x, seed_y;
+    float tile_x, tile_y;
+    float alpha, peak_frequency, wind_speed, angle, depth, swell, detail, spread;
+};
+
+// Push constants of spectrum_modulate.glsl:24-29 and fft_unpack.glsl:20-25 for one cascade update.
+struct CascadeDispatch {
+    int32_t cascade;
+    float tile_x, tile_y, depth, time;
+    float whitecap, foam_grow_rate, foam_decay_rate;
+};
+
+struct DeviceBuffers {
+    int map_size;
+    int num_cascades;
+    float4* spectrum;      // [C][N][N] (Re h0(k), Im h0(k), Re h0(-k), -Im h0(-k))      RGBA32F
+    float4* rowpass;       // [C][2][N][N] (re_a, re_b, im_a, im_b), pair p = layers (2p, 2p+1)
+    uint2* displacement;   // [C][N][N] 4 x half                                          RGBA16F
+    uint2* normal;         // [C][N][N] 4 x half, .a = foam state                         RGBA16F
+    float4* displacement_f32;  // optional taps (nullptr when disabled)
+    float4* normal_f32;
+    const float2* twiddles;    // [kTwiddleCount] global copy of the universal twiddle table
+};
+
+// Opts the kernels of `map_size` into their dynamic shared-memory footprint (once per device).
+cudaError_t configure_kernels(int map_size);
+
+// Computes the universal twiddle table (fft_butterfly.glsl:27) into `twiddles_dev` and into the
+// module's __constant__ copy used for warp-uniform lookups.
+cudaError_t init_twiddles(float2* twiddles_dev, cudaStream_t stream);
+
+// spectrum_compute.glsl for `count` dirty cascades (dispatch records in device memory).
+cudaError_t launch_spectrum_compute(const DeviceBuffers& b, const SpectrumDispatch* dispatch_dev, int count,
+                                    cudaStream_t stream);
+
+// spectrum_modulate + row IFFT (kernel A) and column IFFT + fft_unpack (kernel B) for `count`
+// cascades.  Returns the number of kernels launched through *launched.  `mid` (optional) is
+// recorded between the two kernels (per-kernel timing for bench.py).
+cudaError_t launch_cascade_update(const DeviceBuffers& b, const CascadeDispatch* dispatch_dev, int count,
+                                  cudaStream_t stream, int* launched, cudaEvent_t mid = nullptr);
+
+// De-interleaves one cascade of the row-pass scratch into [4][N][N][2] floats (debug tap).
+cudaError_t launch_rowpass_export(const DeviceBuffers& b, int cascade, float2* out_dev, cudaStream_t stream);
+
+}  // namespace ocean

@@ -1,0 +1,156 @@
+/*
+ * include/ocean.h -- C ABI of libocean.so, the B200-native drop-in for the wave-generation
+ * hot path of 2Retr0/GodotOceanWaves (spectrum -> time propagation -> 4 packed N x N inverse
+ * FFTs -> displacement / normal / Jacobian-foam maps).
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * reference repository).  Everything is plain C: opaque handle, POD structs, raw pointers
+ * and sizes.  Every function returns an int status (OCEAN_OK == 0) and never throws or
+ * aborts; ocean_last_error() returns a thread-local description of the last failure.
+ *
+ * Threading: a generator is NOT thread-safe (the reference runs on Godot's main thread,
+ * assets/water/wave_generator.gd:19).  All GPU work of a generator is issued on its own
+ * CUDA stream; calls are asynchronous w.r.t. the GPU until ocean_synchronize() or a
+ * *_to_host call without the _async suffix.
+ *
+ * Ownership: the library owns all device memory (cf. RenderingContext's DeletionQueue,
+ * assets/render_context.gd:4-21,40-46); callers borrow device pointers that stay valid until
+ * ocean_destroy().  Changing map_size or the cascade count = destroy + create, as in
+ * assets/water/water.gd:22-41,84-91.
+ */
+#ifndef OCEAN_H
+#define OCEAN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCEAN_OK 0
+#define OCEAN_ERR_INVALID_ARGUMENT 1
+#define OCEAN_ERR_CUDA 2
+#define OCEAN_ERR_UNSUPPORTED 3
+#define OCEAN_ERR_STATE 4
+
+#define OCEAN_MAX_MAP_SIZE 1024 /* assets/shaders/compute/fft_compute.glsl:9 */
+#define OCEAN_MIN_MAP_SIZE 128  /* assets/water/water.gd:38, wave_generator.gd:46 */
+
+typedef struct ocean_generator ocean_generator; /* replaces the WaveGenerator node, wave_generator.gd:2 */
+
+/* POD mirror of the WaveCascadeParameters resource, assets/water/wave_cascade_parameters.gd:2-42.
+ * GDScript floats are binary64; Vector2 components are binary32.  The library rounds to
+ * binary32 exactly where RenderingContext.create_push_constant does (render_context.gd:122-135). */
+typedef struct ocean_cascade_params {
+    float tile_length[2];             /* :7   metres */
+    double displacement_scale;        /* :9   render-side only (map_scales, water.gd:102-110) */
+    double normal_scale;              /* :11  render-side only */
+    double wind_speed;                /* :15  m/s, clamped >= 1e-4 by the setter */
+    double wind_direction;            /* :17  degrees */
+    double fetch_length;              /* :20  kilometres, clamped >= 1e-4 */
+    double swell;                     /* :22 */
+    double spread;                    /* :25 */
+    double detail;                    /* :28 */
+    double whitecap;                  /* :32 */
+    double foam_amount;               /* :34 */
+    int32_t spectrum_seed[2];         /* :37 */
+    int32_t should_generate_spectrum; /* :38  dirty flag; cleared by the library when it regenerates */
+    double time;                      /* :40  advanced by ocean_update */
+    double foam_grow_rate;            /* :41  written by ocean_update */
+    double foam_decay_rate;           /* :42  written by ocean_update */
+} ocean_cascade_params;
+
+typedef struct ocean_info {
+    int32_t device;
+    int32_t map_size;
+    int32_t num_cascades;
+    int32_t pending_cascades;      /* pass_num_cascades_remaining, wave_generator.gd:15 */
+    uint64_t kernel_launches;      /* kernels launched by this generator since creation */
+    uint64_t cascade_updates;      /* cascade updates executed since creation */
+    uint64_t device_bytes;         /* device memory owned by the generator */
+} ocean_info;
+
+/* class defaults of wave_cascade_parameters.gd:7-42 */
+int ocean_default_cascade_params(ocean_cascade_params* out);
+
+/* WaveGenerator.map_size + WaveGenerator.init_gpu(num_cascades), wave_generator.gd:8,17-54.
+ * map_size in {128,256,512,1024} (water.gd:38); num_cascades >= 1 (the reference passes
+ * max(2, n), water.gd:91 -- callers may do the same).  Allocates the spectrum (RGBA32F x
+ * layers), the row-pass scratch, the two RGBA16F layered maps and the twiddle table. */
+int ocean_create(int device, int map_size, int num_cascades, ocean_generator** out);
+
+/* NOTIFICATION_PREDELETE -> context.free(), wave_generator.gd:111-113, render_context.gd:40-46 */
+int ocean_destroy(ocean_generator* gen);
+
+/* WaveGenerator.update(delta, parameters), wave_generator.gd:90-109: flushes cascades
+ * 0..remaining-1 left from the previous pass, then time += delta and the foam rates for every
+ * element of parameters[0..count), then arms `count` pending cascades.  `parameters` is in/out
+ * (time, foam rates and the dirty flags of flushed cascades are written back). */
+int ocean_update(ocean_generator* gen, double delta, ocean_cascade_params* parameters, int count);
+
+/* WaveGenerator._process, wave_generator.gd:56-63: runs ONE pending cascade (highest index
+ * first).  If `parameters` is non-NULL the live values are re-read (the reference dereferences the
+ * live Resource objects) and the dirty flag is written back.  No-op when nothing is pending. */
+int ocean_process(ocean_generator* gen, ocean_cascade_params* parameters, int count);
+
+/* Batched fast path: ocean_update() followed by all pending cascades in one fused launch pair
+ * (what `count` rendered frames of _process produce; cascades are independent,
+ * wave_generator.gd:96-97). */
+int ocean_update_all(ocean_generator* gen, double delta, ocean_cascade_params* parameters, int count);
+
+/* descriptors[&'displacement_map'].rid / descriptors[&'normal_map'].rid, wave_generator.gd:34-35,
+ * water.gd:95-96.  Device pointers to [num_cascades][map_size][map_size][4] IEEE half (RGBA16F),
+ * layer-major, tightly packed: displacement = (hx,hy,hz,0), normal = (dy/dx/(1+|dxx|),
+ * dy/dz/(1+|dzz|), dhx_dx, foam) (fft_unpack.glsl:50,66-67). */
+int ocean_get_maps(ocean_generator* gen, void** displacement_dev, void** normal_dev, size_t* layer_bytes);
+
+/* Host hand-off for RenderingDevice.texture_update(rid, layer, bytes) (the maps are created with
+ * TEXTURE_USAGE_CAN_UPDATE_BIT, wave_generator.gd:34-35).  Copies layers [first, first+count).
+ * Either destination may be NULL.  The _async form returns after enqueueing on the generator's
+ * stream (use pinned memory from ocean_host_alloc and ocean_synchronize). */
+int ocean_copy_maps_to_host(ocean_generator* gen, int first, int count, void* displacement_host, void* normal_host);
+int ocean_copy_maps_to_host_async(ocean_generator* gen, int first, int count, void* displacement_host, void* normal_host);
+int ocean_synchronize(ocean_generator* gen);
+int ocean_host_alloc(void** ptr, size_t bytes); /* pinned host memory */
+int ocean_host_free(void* ptr);
+
+/* descriptors[&'spectrum'] (RGBA32F, TEXTURE_USAGE_CAN_COPY_FROM_BIT, wave_generator.gd:31):
+ * [map_size][map_size][4] float = (Re h0(k), Im h0(k), Re h0(-k), -Im h0(-k)) for one cascade. */
+int ocean_copy_spectrum_to_host(ocean_generator* gen, int cascade, float* host);
+
+/* Parity/debug taps (not timed): binary32 maps before the half conversion, the row-pass output
+ * ([4][N][N][2] float, == fft_buffer half 1 after the first fft_compute, wave_generator.gd:79) and
+ * the twiddle table ([N-1][2] float: stage s, index j at (1<<s)-1+j; fft_butterfly.glsl:27). */
+int ocean_enable_f32_taps(ocean_generator* gen, int enable);
+int ocean_copy_f32_maps_to_host(ocean_generator* gen, int cascade, float* displacement_host, float* normal_host);
+int ocean_copy_rowpass_to_host(ocean_generator* gen, int cascade, float* host);
+int ocean_copy_twiddles_to_host(ocean_generator* gen, float* host);
+
+/* Checkpoint/resume of the only frame-to-frame state, normal_map.a (fft_unpack.glsl:61-64):
+ * [map_size][map_size] IEEE half for one cascade. */
+int ocean_get_foam_state(ocean_generator* gen, int cascade, uint16_t* host);
+int ocean_set_foam_state(ocean_generator* gen, int cascade, const uint16_t* host);
+
+/* static func JONSWAP_alpha / JONSWAP_peak_angular_frequency, wave_generator.gd:116-121
+ * (fetch_length in metres, binary64). */
+double ocean_jonswap_alpha(double wind_speed, double fetch_length);
+double ocean_jonswap_peak_angular_frequency(double wind_speed, double fetch_length);
+
+/* Device-side timing on the generator's stream (CUDA events), used by bench.py. */
+int ocean_timer_start(ocean_generator* gen);
+int ocean_timer_stop(ocean_generator* gen, float* elapsed_ms); /* synchronizes */
+
+/* Per-kernel device times of the most recent launch sequence (CUDA events between the kernels):
+ * spectrum generation, kernel A (time propagation + row IFFT), kernel B (column IFFT + maps). */
+int ocean_set_profiling(ocean_generator* gen, int enable);
+int ocean_get_last_kernel_times(ocean_generator* gen, float* spectrum_ms, float* rowpass_ms, float* colpass_ms);
+
+int ocean_get_info(ocean_generator* gen, ocean_info* out);
+const char* ocean_last_error(void);
+const char* ocean_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCEAN_H */

@@ -1,0 +1,101 @@
+"""CPU-side checks of the drop-in boundary: libocean.so loads, exports every symbol include/ocean.h
+declares, fails loudly without a GPU, and the host-side mirrors behave like the reference classes."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import godotoceanwaves_b200 as gow
+from godotoceanwaves_b200 import build as native_build
+from godotoceanwaves_b200 import native
+from oracle import pyoracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    native_build.build_native()
+    return gow.load_library()
+
+
+def test_header_symbols_all_exported(lib):
+    header = open(os.path.join(ROOT, "include", "ocean.h")).read()
+    declared = set(re.findall(r"\b(ocean_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    assert declared == set(native.SIGNATURES), declared ^ set(native.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_struct_layout_matches_header():
+    # 2 floats + 10 doubles + 3 int32 (+pad) + 3 doubles
+    assert C.sizeof(native.CascadeParamsC) == 8 + 80 + 16 + 24
+    assert native.CascadeParamsC.time.offset == 104
+    assert C.sizeof(native.InfoC) == 40
+
+
+def test_jonswap_statics_match_reference_formulas(lib):
+    # wave_generator.gd:116-121, pins from SURVEY 4
+    assert lib.ocean_jonswap_alpha(20.0, 550e3) == pytest.approx(0.009380366716946217, rel=1e-15)
+    assert lib.ocean_jonswap_peak_angular_frequency(20.0, 550e3) == pytest.approx(0.45331955874140006, rel=1e-15)
+    for U, F in [(10, 150e3), (5, 1e3), (30, 1000e3)]:
+        assert lib.ocean_jonswap_alpha(U, F) == po.JONSWAP_alpha(U, F)
+        assert lib.ocean_jonswap_peak_angular_frequency(U, F) == po.JONSWAP_peak_angular_frequency(U, F)
+
+
+def test_defaults_match_wave_cascade_parameters(lib):
+    p = native.CascadeParamsC()
+    assert lib.ocean_default_cascade_params(C.byref(p)) == 0
+    d = gow.WaveCascadeParameters()
+    assert (p.tile_length[0], p.tile_length[1]) == d.tile_length == (50.0, 50.0)
+    for f in ("displacement_scale", "normal_scale", "wind_speed", "wind_direction", "fetch_length", "swell", "spread",
+              "detail", "whitecap", "foam_amount"):
+        assert getattr(p, f) == getattr(d, f), f
+    assert p.should_generate_spectrum == 1 and d.should_generate_spectrum
+
+
+def test_no_cpu_fallback_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    g = gow.WaveGenerator()
+    g.map_size = 256
+    with pytest.raises(gow.OceanError, match="no CPU fallback"):
+        g.init_gpu(2)
+    assert lib.ocean_destroy(None) != 0 and b"NULL" in lib.ocean_last_error()
+    with pytest.raises(gow.OceanError):
+        g.maps_to_host()
+
+
+def test_wave_cascade_parameters_setters():
+    # wave_cascade_parameters.gd:7-35: every setter but the two scales raises the dirty flag; clamps
+    p = gow.WaveCascadeParameters()
+    p.should_generate_spectrum = False
+    p.displacement_scale = 0.5
+    p.normal_scale = 0.5
+    assert not p.should_generate_spectrum
+    for name, val in [("tile_length", (10, 20)), ("wind_speed", 3.0), ("wind_direction", 45.0), ("fetch_length", 10.0),
+                      ("swell", 0.1), ("spread", 0.3), ("detail", 0.9), ("whitecap", 0.7), ("foam_amount", 2.0)]:
+        p.should_generate_spectrum = False
+        setattr(p, name, val)
+        assert p.should_generate_spectrum, name
+    p.wind_speed = -5
+    p.fetch_length = 0
+    assert p.wind_speed == 0.0001 and p.fetch_length == 0.0001
+    c = native.CascadeParamsC()
+    p.spectrum_seed = (3, -4)
+    p.time = 12.5
+    p.to_c(c)
+    assert (c.spectrum_seed[0], c.spectrum_seed[1]) == (3, -4) and c.time == 12.5 and c.tile_length[1] == 20.0
+
+
+def test_push_constant_mirror_matches_oracle_restatement():
+    data = [1234, -5678, 88.0, 88.0, 0.009202510754677472, 0.8807208260620296, 10.0, 0.3490658503988659, 20.0, 0.8,
+            1.0, 0.2, 3]
+    assert gow.RenderingContext.create_push_constant(data) == po.create_push_constant(data)
+    assert len(gow.RenderingContext.create_push_constant(data)) == 64
+    with pytest.raises(AssertionError):
+        gow.RenderingContext.create_push_constant([0.0] * 33)
