@@ -233,7 +233,7 @@ def main():
     reps = min(args.steps, 20)
     for _ in range(reps):
         gen.update_all(delta, params)
-        _, a, b = gen.last_kernel_times()
+        _, a, b, kchunk = gen.last_kernel_times()
         ka += a
         kb += b
     gen.set_profiling(False)
@@ -288,7 +288,7 @@ def main():
                      "traffic": None, "peak_source": peak_src,
                      "kernel": "k_modulate_rowfft + k_colfft_unpack (one step = the launch pair)",
                      "algorithmic_bytes_per_step": ALGO_BYTES_PER_TEXEL * texels_per_step,
-                     "kernel_ms": {"k_modulate_rowfft": ka, "k_colfft_unpack": kb}},
+                     "kernel_ms": {"k_modulate_rowfft": ka, "k_colfft_unpack": kb, "cascades_per_launch": kchunk}},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_s * 1e3 / e2e_steps, "steps": e2e_steps},
         "gpu_launches": int(launches),

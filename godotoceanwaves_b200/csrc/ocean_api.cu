@@ -56,7 +56,8 @@ struct ocean_generator {
     cudaEvent_t ring_done[kRing] = {};
     int ring_next = 0;
     cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
-    cudaEvent_t prof[4] = {};                           // gen-start, A-start, A/B boundary, B-end
+    cudaEvent_t prof[5] = {};                           // gen-start, A-start, after A(chunk 0), end, after B(chunk 0)
+    int prof_chunk = 0;                                 // cascades in the profiled first chunk
     bool profiling = false;
     bool prof_valid = false, prof_had_gen = false;
     std::vector<ocean_cascade_params> pass_parameters;  // wave_generator.gd:14
@@ -154,9 +155,11 @@ int run_cascades(ocean_generator* g, const int* indices, int n) {
     ocean::CascadeDispatch* hc = g->h_cascade + (size_t)slot * g->num_cascades;
     ocean::SpectrumDispatch* hs = g->h_spectrum + (size_t)slot * g->num_cascades;
     int n_dirty = 0;
+    bool fast_math = true;      // branch-free sqrt/div are valid for sane tile lengths only
     for (int k = 0; k < n; ++k) {
         const int i = indices[k];
         ocean_cascade_params& p = g->pass_parameters[i];
+        for (int a = 0; a < 2; ++a) fast_math = fast_math && p.tile_length[a] >= 1e-6f && p.tile_length[a] <= 1e9f;
         if (p.should_generate_spectrum) {                            // :68-72
             hs[n_dirty++] = make_spectrum_dispatch(p, i);
             p.should_generate_spectrum = 0;
@@ -173,11 +176,13 @@ int run_cascades(ocean_generator* g, const int* indices, int n) {
     OCEAN_CUDA(cudaEventRecord(g->ring_done[slot], g->stream));
     int launched = 0;
     if (g->profiling) OCEAN_CUDA(cudaEventRecord(g->prof[1], g->stream));
-    OCEAN_CUDA(ocean::launch_cascade_update(g->buf, g->d_cascade, n, g->stream, &launched, g->profiling ? g->prof[2] : nullptr));
+    OCEAN_CUDA(ocean::launch_cascade_update(g->buf, g->d_cascade, n, fast_math, g->stream, &launched, g->profiling ? g->prof[2] : nullptr, g->profiling ? g->prof[4] : nullptr));
     if (g->profiling) {
         OCEAN_CUDA(cudaEventRecord(g->prof[3], g->stream));
         g->prof_valid = true;
         g->prof_had_gen = n_dirty != 0;
+        const int ch = ocean::chunk_cascades(g->map_size);
+        g->prof_chunk = n < ch ? n : ch;
     }
     g->kernel_launches += (uint64_t)launched;
     g->cascade_updates += (uint64_t)n;
@@ -528,7 +533,7 @@ int ocean_set_profiling(ocean_generator* gen, int enable) {
     return OCEAN_OK;
 }
 
-int ocean_get_last_kernel_times(ocean_generator* gen, float* spectrum_ms, float* rowpass_ms, float* colpass_ms) {
+int ocean_get_last_kernel_times(ocean_generator* gen, float* spectrum_ms, float* rowpass_ms, float* colpass_ms, int* chunk_cascades) {
     int rc = check_gen(gen);
     if (rc) return rc;
     if (!gen->prof_valid) return fail(OCEAN_ERR_STATE, "no profiled launch yet; call ocean_set_profiling(gen, 1) and run an update");
@@ -536,7 +541,26 @@ int ocean_get_last_kernel_times(ocean_generator* gen, float* spectrum_ms, float*
     float t = 0.f;
     if (spectrum_ms) { OCEAN_CUDA(cudaEventElapsedTime(&t, gen->prof[0], gen->prof[1])); *spectrum_ms = gen->prof_had_gen ? t : 0.f; }
     if (rowpass_ms) OCEAN_CUDA(cudaEventElapsedTime(rowpass_ms, gen->prof[1], gen->prof[2]));
-    if (colpass_ms) OCEAN_CUDA(cudaEventElapsedTime(colpass_ms, gen->prof[2], gen->prof[3]));
+    if (colpass_ms) OCEAN_CUDA(cudaEventElapsedTime(colpass_ms, gen->prof[2], gen->prof[4]));
+    if (chunk_cascades) *chunk_cascades = gen->prof_chunk;
+    return OCEAN_OK;
+}
+
+int ocean_selftest_math(ocean_generator* gen, uint64_t* failures, uint64_t* tested) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    if (!failures || !tested) return fail(OCEAN_ERR_INVALID_ARGUMENT, "NULL argument");
+    unsigned long long* d = nullptr;
+    OCEAN_CUDA(cudaMalloc(reinterpret_cast<void**>(&d), 2 * sizeof(unsigned long long)));
+    OCEAN_CUDA(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), gen->stream));
+    OCEAN_CUDA(ocean::launch_selftest_math(d, d + 1, gen->stream));
+    gen->kernel_launches += 1;
+    unsigned long long h[2] = {0, 0};
+    OCEAN_CUDA(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, gen->stream));
+    OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+    cudaFree(d);
+    *failures = h[0];
+    *tested = h[1];
     return OCEAN_OK;
 }
 

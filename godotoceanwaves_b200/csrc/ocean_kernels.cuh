@@ -48,10 +48,16 @@ cudaError_t launch_spectrum_compute(const DeviceBuffers& b, const SpectrumDispat
                                     cudaStream_t stream);
 
 // spectrum_modulate + row IFFT (kernel A) and column IFFT + fft_unpack (kernel B) for `count`
-// cascades.  Returns the number of kernels launched through *launched.  `mid` (optional) is
-// recorded between the two kernels (per-kernel timing for bench.py).
-cudaError_t launch_cascade_update(const DeviceBuffers& b, const CascadeDispatch* dispatch_dev, int count,
-                                  cudaStream_t stream, int* launched, cudaEvent_t mid = nullptr);
+// cascades, issued as L2-sized chunks (chunk_cascades) of one launch pair each.  `fast_math` selects the
+// branch-free correctly-rounded sqrt/div (valid when every tile_length is within [1e-6, 1e9] m).
+// Returns the number of kernels launched through *launched.  `mid` / `mid2` (optional) are recorded
+// after kernel A / kernel B of the FIRST chunk (per-kernel timing for bench.py).
+cudaError_t launch_cascade_update(const DeviceBuffers& b, const CascadeDispatch* dispatch_dev, int count, bool fast_math,
+                                  cudaStream_t stream, int* launched, cudaEvent_t mid = nullptr, cudaEvent_t mid2 = nullptr);
+int chunk_cascades(int map_size);
+
+// Compares the branch-free sqrt/div with __fsqrt_rn/__fdiv_rn on the device (debug entry point).
+cudaError_t launch_selftest_math(unsigned long long* failures_dev, unsigned long long* tested_dev, cudaStream_t stream);
 
 // De-interleaves one cascade of the row-pass scratch into [4][N][N][2] floats (debug tap).
 cudaError_t launch_rowpass_export(const DeviceBuffers& b, int cascade, float2* out_dev, cudaStream_t stream);

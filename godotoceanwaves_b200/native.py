@@ -58,7 +58,8 @@ SIGNATURES = {
     "ocean_timer_start": (C.c_int, [_H]),
     "ocean_timer_stop": (C.c_int, [_H, _P(C.c_float)]),
     "ocean_set_profiling": (C.c_int, [_H, C.c_int]),
-    "ocean_get_last_kernel_times": (C.c_int, [_H, _P(C.c_float), _P(C.c_float), _P(C.c_float)]),
+    "ocean_get_last_kernel_times": (C.c_int, [_H, _P(C.c_float), _P(C.c_float), _P(C.c_float), _P(C.c_int)]),
+    "ocean_selftest_math": (C.c_int, [_H, _P(C.c_uint64), _P(C.c_uint64)]),
     "ocean_get_info": (C.c_int, [_H, _P(InfoC)]),
     "ocean_last_error": (C.c_char_p, []),
     "ocean_version": (C.c_char_p, []),

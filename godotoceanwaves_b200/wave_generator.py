@@ -204,7 +204,8 @@ class WaveGenerator:
         check(load_library().ocean_set_profiling(self.context, 1 if enable else 0))
 
     def last_kernel_times(self):
-        """(spectrum_ms, rowpass_ms, colpass_ms) of the most recent launch sequence."""
-        a, b, c = C.c_float(), C.c_float(), C.c_float()
-        check(load_library().ocean_get_last_kernel_times(self.context, C.byref(a), C.byref(b), C.byref(c)))
-        return a.value, b.value, c.value
+        """(spectrum_ms, rowpass_ms, colpass_ms, chunk_cascades) of the most recent launch sequence; the two
+        kernel times are those of the first L2-sized chunk of `chunk_cascades` cascades."""
+        a, b, c, n = C.c_float(), C.c_float(), C.c_float(), C.c_int()
+        check(load_library().ocean_get_last_kernel_times(self.context, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+        return a.value, b.value, c.value, n.value

@@ -142,9 +142,15 @@ int ocean_timer_start(ocean_generator* gen);
 int ocean_timer_stop(ocean_generator* gen, float* elapsed_ms); /* synchronizes */
 
 /* Per-kernel device times of the most recent launch sequence (CUDA events between the kernels):
- * spectrum generation, kernel A (time propagation + row IFFT), kernel B (column IFFT + maps). */
+ * spectrum generation, then kernel A (time propagation + row IFFT) and kernel B (column IFFT + maps)
+ * of the FIRST L2-sized chunk, whose cascade count is returned through chunk_cascades. */
 int ocean_set_profiling(ocean_generator* gen, int enable);
-int ocean_get_last_kernel_times(ocean_generator* gen, float* spectrum_ms, float* rowpass_ms, float* colpass_ms);
+int ocean_get_last_kernel_times(ocean_generator* gen, float* spectrum_ms, float* rowpass_ms, float* colpass_ms,
+                                int* chunk_cascades);
+
+/* Device self-test: the kernels' branch-free correctly-rounded sqrt/div against the IEEE intrinsics
+ * (every binary32 in [2^-100, 2^100] for sqrt, ~1.2e9 random pairs for div). */
+int ocean_selftest_math(ocean_generator* gen, uint64_t* failures, uint64_t* tested);
 
 int ocean_get_info(ocean_generator* gen, ocean_info* out);
 const char* ocean_last_error(void);
