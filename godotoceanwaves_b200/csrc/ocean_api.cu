@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -60,6 +61,10 @@ struct ocean_generator {
     int prof_chunk = 0;                                 // cascades in the profiled first chunk
     bool profiling = false;
     bool prof_valid = false, prof_had_gen = false;
+    int* d_queue = nullptr;                             // [1 + num_cascades] work counter + completion counters
+    std::vector<int> done_count;                        // host mirror of the completion counters
+    int resident_ctas = 0;
+    bool persistent = true;                             // OCEAN_PIPELINE=split selects the two-kernel path
     std::vector<ocean_cascade_params> pass_parameters;  // wave_generator.gd:14
     int pass_num_cascades_remaining = 0;                // wave_generator.gd:15
     uint64_t kernel_launches = 0;
@@ -97,6 +102,7 @@ void release(ocean_generator* g) {
     cudaFree(g->export_buf);
     cudaFree(g->d_cascade);
     cudaFree(g->d_spectrum);
+    cudaFree(g->d_queue);
     if (g->h_cascade) cudaFreeHost(g->h_cascade);
     if (g->h_spectrum) cudaFreeHost(g->h_spectrum);
     for (auto& ev : g->ring_done)
@@ -142,6 +148,7 @@ ocean::CascadeDispatch make_cascade_dispatch(const ocean_cascade_params& p, int 
     d.whitecap = (float)p.whitecap;
     d.foam_grow_rate = (float)p.foam_grow_rate;
     d.foam_decay_rate = (float)p.foam_decay_rate;
+    d.done_target = 0;
     return d;
 }
 
@@ -165,6 +172,8 @@ int run_cascades(ocean_generator* g, const int* indices, int n) {
             p.should_generate_spectrum = 0;
         }
         hc[k] = make_cascade_dispatch(p, i);                         // :73,85
+        g->done_count[i] += ocean::a_items_per_cascade(g->map_size);
+        hc[k].done_target = g->done_count[i];
     }
     if (g->profiling) OCEAN_CUDA(cudaEventRecord(g->prof[0], g->stream));
     if (n_dirty) {
@@ -176,7 +185,14 @@ int run_cascades(ocean_generator* g, const int* indices, int n) {
     OCEAN_CUDA(cudaEventRecord(g->ring_done[slot], g->stream));
     int launched = 0;
     if (g->profiling) OCEAN_CUDA(cudaEventRecord(g->prof[1], g->stream));
-    OCEAN_CUDA(ocean::launch_cascade_update(g->buf, g->d_cascade, n, fast_math, g->stream, &launched, g->profiling ? g->prof[2] : nullptr, g->profiling ? g->prof[4] : nullptr));
+    if (g->persistent && !g->profiling) {
+        OCEAN_CUDA(ocean::launch_cascade_update_persistent(g->buf, g->d_cascade, n, fast_math, g->stream, g->d_queue, g->resident_ctas));
+        launched = 1;
+    } else {
+        OCEAN_CUDA(ocean::launch_cascade_update(g->buf, g->d_cascade, n, fast_math, g->stream, &launched, g->profiling ? g->prof[2] : nullptr, g->profiling ? g->prof[4] : nullptr));
+        // keep the device-side completion counters in step with the host mirror (one small copy)
+        OCEAN_CUDA(cudaMemcpyAsync(g->d_queue + 1, g->done_count.data(), sizeof(int) * g->done_count.size(), cudaMemcpyHostToDevice, g->stream));
+    }
     if (g->profiling) {
         OCEAN_CUDA(cudaEventRecord(g->prof[3], g->stream));
         g->prof_valid = true;
@@ -282,6 +298,13 @@ int ocean_create(int device, int map_size, int num_cascades, ocean_generator** o
     CREATE_CUDA(dev_alloc(g, &g->twiddles, (size_t)ocean::kTwiddleCount + 1));   // :32
     CREATE_CUDA(dev_alloc(g, &g->d_cascade, C));
     CREATE_CUDA(dev_alloc(g, &g->d_spectrum, C));
+    CREATE_CUDA(dev_alloc(g, &g->d_queue, C + 1));
+    CREATE_CUDA(cudaMemsetAsync(g->d_queue, 0, sizeof(int) * (C + 1), g->stream));
+    g->done_count.assign(C, 0);
+    {
+        const char* mode = std::getenv("OCEAN_PIPELINE");
+        g->persistent = !(mode && std::strcmp(mode, "split") == 0);
+    }
     CREATE_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g->h_cascade), sizeof(ocean::CascadeDispatch) * kRing * C, cudaHostAllocDefault));
     CREATE_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g->h_spectrum), sizeof(ocean::SpectrumDispatch) * kRing * C, cudaHostAllocDefault));
     for (auto& ev : g->ring_done) CREATE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -297,6 +320,7 @@ int ocean_create(int device, int map_size, int num_cascades, ocean_generator** o
     g->buf.num_cascades = num_cascades;
     g->buf.twiddles = g->twiddles;
     CREATE_CUDA(ocean::configure_kernels(map_size));
+    CREATE_CUDA(ocean::persistent_grid_size(map_size, &g->resident_ctas));
     CREATE_CUDA(ocean::init_twiddles(g->twiddles, g->stream));            // fft_butterfly once, :52-54
     g->kernel_launches += 1;
     CREATE_CUDA(cudaStreamSynchronize(g->stream));

@@ -22,6 +22,7 @@ struct CascadeDispatch {
     int32_t cascade;
     float tile_x, tile_y, depth, time;
     float whitecap, foam_grow_rate, foam_decay_rate;
+    int32_t done_target;   // persistent kernel: value of done[cascade] once this update's row pass is complete
 };
 
 struct DeviceBuffers {
@@ -55,6 +56,15 @@ cudaError_t launch_spectrum_compute(const DeviceBuffers& b, const SpectrumDispat
 cudaError_t launch_cascade_update(const DeviceBuffers& b, const CascadeDispatch* dispatch_dev, int count, bool fast_math,
                                   cudaStream_t stream, int* launched, cudaEvent_t mid = nullptr, cudaEvent_t mid2 = nullptr);
 int chunk_cascades(int map_size);
+
+// Same work as launch_cascade_update in ONE persistent launch (work queue over A and B items, B items
+// wait on per-cascade completion counters).  queue_dev: [0] = work counter, [1 + c] = completion counter of
+// cascade c (monotonic; dispatch[i].done_target is the value to wait for).  resident_ctas from
+// persistent_grid_size().
+cudaError_t launch_cascade_update_persistent(const DeviceBuffers& b, const CascadeDispatch* dispatch_dev, int count, bool fast_math,
+                                             cudaStream_t stream, int* queue_dev, int resident_ctas);
+cudaError_t persistent_grid_size(int map_size, int* out);
+int a_items_per_cascade(int map_size);
 
 // Compares the branch-free sqrt/div with __fsqrt_rn/__fdiv_rn on the device (debug entry point).
 cudaError_t launch_selftest_math(unsigned long long* failures_dev, unsigned long long* tested_dev, cudaStream_t stream);
