@@ -101,7 +101,7 @@ __device__ __forceinline__ void stockham_stage(const C2 (&in)[R], C2 (&out)[R], 
         } else {
             float2 tw;
             if (LS0 == 0) tw = c_twiddles[BASE + jl];                  // warp-uniform: constant bank
-            else tw = __ldg(&tw_g[BASE + j + (jl << LS0)]);
+            else tw = tw_g[BASE + j + (jl << LS0)];                    // table copy in shared memory
 #pragma unroll
             for (int il = 0; il < ML; ++il)
                 butterfly(in[SL * il + jl], in[SL * (il + ML) + jl], tw, out[SL * 2 * il + jl], out[SL * (2 * il + 1) + jl]);
