@@ -12,26 +12,46 @@
 namespace detmath {
 
 // ---- sin/cos: two-term Cody-Waite by pi/2 (33-bit head), Taylor kernels on |r|<=pi/4 ----
+// The constants live in constant memory: a binary64 immediate costs two UMOVs per use, a constant-bank
+// operand costs one uniform load that the compiler can hoist out of loops.
+__constant__ double c_sincos[16] = {
+    0x1.45f306dc9c883p-1,    // [0]  2/pi
+    0x1.921fb54400000p+0,    // [1]  pi/2 head (33 bits)
+    0x1.0b4611a626331p-34,   // [2]  pi/2 tail
+    0x1.6124613a86d09p-33,   // [3]  sin:  1/13!
+    -0x1.ae64567f544e4p-26,  // [4]       -1/11!
+    0x1.71de3a556c734p-19,   // [5]        1/9!
+    -0x1.a01a01a01a01ap-13,  // [6]       -1/7!
+    0x1.1111111111111p-7,    // [7]        1/5!
+    -0x1.5555555555555p-3,   // [8]       -1/3!
+    -0x1.93974a8c07c9dp-37,  // [9]  cos: -1/14!
+    0x1.1eed8eff8d898p-29,   // [10]       1/12!
+    -0x1.27e4fb7789f5cp-22,  // [11]      -1/10!
+    0x1.a01a01a01a01ap-16,   // [12]       1/8!
+    -0x1.6c16c16c16c17p-10,  // [13]      -1/6!
+    0x1.5555555555555p-5,    // [14]       1/4!
+    -0x1.0000000000000p-1 }; // [15]      -1/2!
+
 __device__ __forceinline__ void sincos64(double x, double& s, double& c) {
-    const double fn = rint(x * 0x1.45f306dc9c883p-1);
-    double r = fma(-fn, 0x1.921fb54400000p+0, x);
-    r = fma(-fn, 0x1.0b4611a626331p-34, r);
+    const double fn = rint(x * c_sincos[0]);
+    double r = fma(-fn, c_sincos[1], x);
+    r = fma(-fn, c_sincos[2], r);
     const int q = (int)(((long long)fn) & 3);
     const double z = r * r;
-    double ps = 0x1.6124613a86d09p-33;
-    ps = fma(ps, z, -0x1.ae64567f544e4p-26);
-    ps = fma(ps, z, 0x1.71de3a556c734p-19);
-    ps = fma(ps, z, -0x1.a01a01a01a01ap-13);
-    ps = fma(ps, z, 0x1.1111111111111p-7);
-    ps = fma(ps, z, -0x1.5555555555555p-3);
+    double ps = c_sincos[3];
+    ps = fma(ps, z, c_sincos[4]);
+    ps = fma(ps, z, c_sincos[5]);
+    ps = fma(ps, z, c_sincos[6]);
+    ps = fma(ps, z, c_sincos[7]);
+    ps = fma(ps, z, c_sincos[8]);
     const double sr = fma(r * z, ps, r);
-    double pc = -0x1.93974a8c07c9dp-37;
-    pc = fma(pc, z, 0x1.1eed8eff8d898p-29);
-    pc = fma(pc, z, -0x1.27e4fb7789f5cp-22);
-    pc = fma(pc, z, 0x1.a01a01a01a01ap-16);
-    pc = fma(pc, z, -0x1.6c16c16c16c17p-10);
-    pc = fma(pc, z, 0x1.5555555555555p-5);
-    pc = fma(pc, z, -0x1.0000000000000p-1);
+    double pc = c_sincos[9];
+    pc = fma(pc, z, c_sincos[10]);
+    pc = fma(pc, z, c_sincos[11]);
+    pc = fma(pc, z, c_sincos[12]);
+    pc = fma(pc, z, c_sincos[13]);
+    pc = fma(pc, z, c_sincos[14]);
+    pc = fma(pc, z, c_sincos[15]);
     const double cr = fma(z, pc, 1.0);
     const double s0 = (q & 1) ? cr : sr;
     const double c0 = (q & 1) ? sr : cr;
