@@ -201,10 +201,15 @@ def main():
     N = args.map_size
     C = args.sets * args.cascades_per_set                 # cascades resident on this GPU (weak scaling)
     texels_per_step = C * N * N
-    gen = gow.WaveGenerator(device=local_rank)
-    gen.map_size = N
-    gen.init_gpu(C)
-    params = [synth_params(gow.WaveCascadeParameters, rank * C + c) for c in range(C)]
+    # cascade-parallel split: the global batch of world*C cascades is dealt round-robin over the
+    # ranks, every rank keeps its C cascades resident; no data-path collective.
+    from godotoceanwaves_b200.sharding import ShardedWaveGenerator
+    all_params = [synth_params(gow.WaveCascadeParameters, c) for c in range(world * C)]
+    shard = ShardedWaveGenerator(N, rank=rank, world=world, device=local_rank)
+    shard.update_all(1.0 / 50.0, all_params)      # creates the local generator and the spectra
+    gen = shard.gen
+    params = [all_params[i] for i in shard.owned]
+    assert len(params) == C
     delta = 1.0 / 50.0
 
     # ---- warm-up (first step also generates the spectra) ----

@@ -274,3 +274,21 @@ def test_error_behaviour():
         g.spectrum_to_host(7)
     g._process(0.0)                                                            # nothing pending: no-op
     g.free()
+
+
+def test_multi_gpu_sharded_equals_single_gpu():
+    """cascade-sharded over every visible GPU == single GPU, bit for bit (needs >= 2 GPUs)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus N)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    world = min(ngpu, 8)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "tests", "_sharding_gpu_worker.py")]
+    res = subprocess.run(cmd, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         text=True, timeout=600)
+    assert res.returncode == 0 and "SHARDING_GPU_OK" in res.stdout, res.stdout[-3000:]
