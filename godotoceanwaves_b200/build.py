@@ -34,11 +34,13 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_native(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into godotoceanwaves_b200/libocean.so. No-op when up to date."""
-    if not force and not is_stale():
+def build_native(force: bool = False, verbose: bool = False, out: str | None = None, defines=()) -> str:
+    """Compile csrc/*.cu into godotoceanwaves_b200/libocean.so. No-op when up to date.
+    `out`/`defines` build a tuning variant next to it (loaded with OCEAN_LIB=...)."""
+    if out is None and not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    target = out or LIB_PATH
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", target] + [os.path.join(CSRC, s) for s in SOURCES]
     if os.path.exists("/usr/bin/g++"):
         cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
     if verbose:
@@ -48,7 +50,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout)
     if verbose:
         print(res.stdout)
-    return LIB_PATH
+    return target
 
 
 if __name__ == "__main__":

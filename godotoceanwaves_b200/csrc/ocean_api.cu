@@ -13,6 +13,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <map>
 #include <vector>
 
 namespace {
@@ -64,6 +65,7 @@ struct ocean_generator {
     int* d_queue = nullptr;                             // [1 + num_cascades] work counter + completion counters
     std::vector<int> done_count;                        // host mirror of the completion counters
     int resident_ctas = 0;
+    std::map<int, std::pair<int*, int>> item_tables;    // cascades per launch -> (device item table, item count)
     bool persistent = true;                             // OCEAN_PIPELINE=split selects the two-kernel path
     std::vector<ocean_cascade_params> pass_parameters;  // wave_generator.gd:14
     int pass_num_cascades_remaining = 0;                // wave_generator.gd:15
@@ -103,6 +105,7 @@ void release(ocean_generator* g) {
     cudaFree(g->d_cascade);
     cudaFree(g->d_spectrum);
     cudaFree(g->d_queue);
+    for (auto& kv : g->item_tables) cudaFree(kv.second.first);
     if (g->h_cascade) cudaFreeHost(g->h_cascade);
     if (g->h_spectrum) cudaFreeHost(g->h_spectrum);
     for (auto& ev : g->ring_done)
@@ -186,8 +189,25 @@ int run_cascades(ocean_generator* g, const int* indices, int n) {
     int launched = 0;
     if (g->profiling) OCEAN_CUDA(cudaEventRecord(g->prof[1], g->stream));
     if (g->persistent && !g->profiling) {
-        OCEAN_CUDA(ocean::launch_cascade_update_persistent(g->buf, g->d_cascade, n, fast_math, g->stream, g->d_queue, g->resident_ctas));
-        launched = 1;
+        // one persistent launch per <= kMaxPersistentCascades cascades (their dispatch records travel by value)
+        for (int first = 0; first < n; first += ocean::kMaxPersistentCascades) {
+            const int m = (n - first < ocean::kMaxPersistentCascades) ? n - first : ocean::kMaxPersistentCascades;
+            auto it = g->item_tables.find(m);
+            if (it == g->item_tables.end()) {
+                const int group = ocean::persistent_group(g->map_size);
+                const int total = ocean::build_item_table(g->map_size, m, group, nullptr);
+                std::vector<int> host((size_t)total);
+                ocean::build_item_table(g->map_size, m, group, host.data());
+                int* dev = nullptr;
+                OCEAN_CUDA(dev_alloc(g, &dev, (size_t)total));
+                OCEAN_CUDA(cudaMemcpyAsync(dev, host.data(), sizeof(int) * (size_t)total, cudaMemcpyHostToDevice, g->stream));
+                OCEAN_CUDA(cudaStreamSynchronize(g->stream));          // host vector goes out of scope
+                it = g->item_tables.emplace(m, std::make_pair(dev, total)).first;
+            }
+            OCEAN_CUDA(ocean::launch_cascade_update_persistent(g->buf, hc + first, m, fast_math, g->stream, g->d_queue,
+                                                               it->second.first, it->second.second, g->resident_ctas));
+            launched += 1;
+        }
     } else {
         OCEAN_CUDA(ocean::launch_cascade_update(g->buf, g->d_cascade, n, fast_math, g->stream, &launched, g->profiling ? g->prof[2] : nullptr, g->profiling ? g->prof[4] : nullptr));
         // keep the device-side completion counters in step with the host mirror (one small copy)

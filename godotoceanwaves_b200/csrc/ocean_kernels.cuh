@@ -58,11 +58,16 @@ cudaError_t launch_cascade_update(const DeviceBuffers& b, const CascadeDispatch*
 int chunk_cascades(int map_size);
 
 // Same work as launch_cascade_update in ONE persistent launch (work queue over A and B items, B items
-// wait on per-cascade completion counters).  queue_dev: [0] = work counter, [1 + c] = completion counter of
-// cascade c (monotonic; dispatch[i].done_target is the value to wait for).  resident_ctas from
-// persistent_grid_size().
-cudaError_t launch_cascade_update_persistent(const DeviceBuffers& b, const CascadeDispatch* dispatch_dev, int count, bool fast_math,
-                                             cudaStream_t stream, int* queue_dev, int resident_ctas);
+// wait on per-cascade completion counters).  `dispatch_host` (<= kMaxPersistentCascades records) travels by
+// value as a kernel parameter (constant bank).  queue_dev: [0] = work counter, [1 + c] = completion counter of
+// cascade c (monotonic; dispatch[i].done_target is the value to wait for).  item_table_dev/total_items from
+// build_item_table(map_size, count, persistent_group(map_size)); resident_ctas from persistent_grid_size().
+constexpr int kMaxPersistentCascades = 256;
+cudaError_t launch_cascade_update_persistent(const DeviceBuffers& b, const CascadeDispatch* dispatch_host, int count, bool fast_math,
+                                             cudaStream_t stream, int* queue_dev, const int* item_table_dev, int total_items,
+                                             int resident_ctas);
+int build_item_table(int map_size, int count, int group, int* out);
+int persistent_group(int map_size);
 cudaError_t persistent_grid_size(int map_size, int* out);
 int a_items_per_cascade(int map_size);
 
