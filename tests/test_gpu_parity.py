@@ -276,6 +276,42 @@ def test_error_behaviour():
     g.free()
 
 
+EDGE_CASES = {
+    "anisotropic_tile": dict(tile_length=(93.0, 41.0)),
+    "detail_damped_zeros": dict(detail=0.35, tile_length=(16.0, 16.0)),       # exp(-(1-detail)^2 k^2) underflows to exact 0
+    "wind_negative_dir": dict(wind_direction=-135.0, wind_speed=3.0, fetch_length=2.0),
+    "wind_360": dict(wind_direction=360.0, spread=1.0),
+    "no_spread_swell2": dict(spread=0.0, swell=2.0),
+    "shallow_long_waves": dict(tile_length=(4000.0, 4000.0)),                   # tanh(k*depth) < 1 on most texels
+    "tiny_tile": dict(tile_length=(0.5, 0.5)),
+    "whitecap_high_foam_max": dict(whitecap=1.6, foam_amount=10.0),
+    "seed_wrap": dict(spectrum_seed=(-10000, 2147483600)),                      # uvec2(id + seed) wraps
+    "late_time": dict(time=36000.0),
+    "calm": dict(wind_speed=0.0001, fetch_length=0.0001),
+}
+
+
+@pytest.mark.parametrize("name", sorted(EDGE_CASES))
+def test_edge_case_parameters(name):
+    """Parameter corners of wave_cascade_parameters.gd (clamps, ranges of the @export_range sliders and beyond)
+    through three updates at 128x128; textures must equal the oracle's (sign of exact zeros aside)."""
+    gow = _gpu()
+    N = 128
+    over = EDGE_CASES[name]
+    pg, pcpu = _pair(gow.WaveCascadeParameters, 2, **over)
+    g = gow.WaveGenerator(); g.map_size = N
+    o = po.OracleWaveGenerator(N)
+    for delta in (0.02, 0.0, 0.031):
+        g.update_all(delta, pg); o.update_all(delta, pcpu)
+    d16, n16 = g.maps_to_host(0, 2)
+    for c in range(2):
+        assert _same_values(d16[c].astype(np.float32), o.displacement_half()[c].astype(np.float32)), (name, c)
+        assert _same_values(n16[c].astype(np.float32), o.normal_half()[c].astype(np.float32)), (name, c)
+    if name not in ("calm",):
+        assert np.isfinite(d16.astype(np.float32)).all()
+    g.free()
+
+
 def test_multi_gpu_sharded_equals_single_gpu():
     """cascade-sharded over every visible GPU == single GPU, bit for bit (needs >= 2 GPUs)."""
     import os
