@@ -160,8 +160,34 @@ __device__ __forceinline__ double atan2_64(double y, double x) {   // atan2(0,0)
 }
 
 // ---- binary32 front-ends (one rounding) ----
+// binary32 sin/cos of a binary32 argument.  Same value as rounding sincos64's outputs: the quadrant swap and
+// negation commute with the (sign-symmetric) rounding, so they are applied to the two rounded kernel values.
 __device__ __forceinline__ void sincosf_det(float x, float& s, float& c) {
-    double ds, dc; sincos64((double)x, ds, dc); s = (float)ds; c = (float)dc;
+    const double xd = (double)x;
+    const double fn = rint(xd * c_sincos[0]);
+    double r = fma(-fn, c_sincos[1], xd);
+    r = fma(-fn, c_sincos[2], r);
+    const int q = (int)(((long long)fn) & 3);
+    const double z = r * r;
+    double ps = c_sincos[3];
+    ps = fma(ps, z, c_sincos[4]);
+    ps = fma(ps, z, c_sincos[5]);
+    ps = fma(ps, z, c_sincos[6]);
+    ps = fma(ps, z, c_sincos[7]);
+    ps = fma(ps, z, c_sincos[8]);
+    const float sr = (float)fma(r * z, ps, r);
+    double pc = c_sincos[9];
+    pc = fma(pc, z, c_sincos[10]);
+    pc = fma(pc, z, c_sincos[11]);
+    pc = fma(pc, z, c_sincos[12]);
+    pc = fma(pc, z, c_sincos[13]);
+    pc = fma(pc, z, c_sincos[14]);
+    pc = fma(pc, z, c_sincos[15]);
+    const float cr = (float)fma(z, pc, 1.0);
+    const float s0 = (q & 1) ? cr : sr;
+    const float c0 = (q & 1) ? sr : cr;
+    s = (q & 2) ? -s0 : s0;
+    c = ((q + 1) & 2) ? -c0 : c0;
 }
 __device__ __forceinline__ float cosf_det(float x) { double s, c; sincos64((double)x, s, c); return (float)c; }
 __device__ __forceinline__ float expf_det(float x) { return (float)exp64((double)x); }
