@@ -339,6 +339,7 @@ int ocean_create(int device, int map_size, int num_cascades, ocean_generator** o
     g->buf.map_size = map_size;
     g->buf.num_cascades = num_cascades;
     g->buf.twiddles = g->twiddles;
+    CREATE_CUDA(ocean::make_rowpass_tensor_map(g->buf.rowpass, map_size, num_cascades, &g->buf.rowpass_tmap));
     CREATE_CUDA(ocean::configure_kernels(map_size));
     CREATE_CUDA(ocean::persistent_grid_size(map_size, &g->resident_ctas));
     CREATE_CUDA(ocean::init_twiddles(g->twiddles, g->stream));            // fft_butterfly once, :52-54

@@ -2,6 +2,7 @@
 // sm_100a kernels (ocean_kernels.cu).  Internal; the public surface is include/ocean.h.
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace ocean {
@@ -35,7 +36,11 @@ struct DeviceBuffers {
     float4* displacement_f32;  // optional taps (nullptr when disabled)
     float4* normal_f32;
     const float2* twiddles;    // [kTwiddleCount] global copy of the universal twiddle table
+    alignas(64) CUtensorMap rowpass_tmap;   // TMA descriptor of `rowpass` (kernel B panel loads)
 };
+
+// Builds the TMA descriptor of the row-pass scratch (driver entry point cuTensorMapEncodeTiled).
+cudaError_t make_rowpass_tensor_map(void* rowpass, int map_size, int num_cascades, CUtensorMap* out);
 
 // Opts the kernels of `map_size` into their dynamic shared-memory footprint (once per device).
 cudaError_t configure_kernels(int map_size);
