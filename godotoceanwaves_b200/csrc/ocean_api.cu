@@ -140,6 +140,31 @@ ocean::SpectrumDispatch make_spectrum_dispatch(const ocean_cascade_params& p, in
     return d;
 }
 
+// DETMATH exp of a binary32 argument (DESIGN.md "DETMATH", same operation sequence as detmath::exp64 in
+// detmath.cuh): clamp to [-110, 90], n = rint(x*log2e), two-term ln2 reduction, Taylor polynomial to r^13 in
+// binary64, one rounding to binary32.  Evaluated here because exp(-foam_decay_rate) (fft_unpack.glsl:62) is
+// uniform per dispatch; std::fma is the exact fused operation, so host and device agree bit for bit.
+float exp_det_host(float xf) {
+    double x = (double)xf;
+    if (x != x) return xf;
+    if (x < -110.0) x = -110.0;
+    if (x > 90.0) x = 90.0;
+    const double fn = std::nearbyint(x * 0x1.71547652b82fep+0);   // default rounding mode: ties to even, like rint() on the device
+    double r = std::fma(-fn, 0x1.62e42ff000000p-1, x);
+    r = std::fma(-fn, -0x1.718432a1b0e26p-35, r);
+    static const double c[12] = {0x1.1eed8eff8d898p-29, 0x1.ae64567f544e4p-26, 0x1.27e4fb7789f5cp-22, 0x1.71de3a556c734p-19,
+                                 0x1.a01a01a01a01ap-16, 0x1.a01a01a01a01ap-13, 0x1.6c16c16c16c17p-10, 0x1.1111111111111p-7,
+                                 0x1.5555555555555p-5,  0x1.5555555555555p-3,  0x1.0000000000000p-1,  0.0};
+    double p = 0x1.6124613a86d09p-33;
+    for (int i = 0; i < 11; ++i) p = std::fma(p, r, c[i]);
+    volatile double rr = r * r;                                    // a separately rounded product, never contracted
+    const double e = std::fma(rr, p, r) + 1.0;
+    const long long sb = ((long long)fn + 1023LL) << 52;
+    double scale;
+    std::memcpy(&scale, &sb, sizeof scale);
+    return (float)(e * scale);
+}
+
 // Push constants of wave_generator.gd:73 (spectrum_modulate) and :85 (fft_unpack).
 ocean::CascadeDispatch make_cascade_dispatch(const ocean_cascade_params& p, int cascade) {
     ocean::CascadeDispatch d;
@@ -150,7 +175,7 @@ ocean::CascadeDispatch make_cascade_dispatch(const ocean_cascade_params& p, int 
     d.time = (float)p.time;
     d.whitecap = (float)p.whitecap;
     d.foam_grow_rate = (float)p.foam_grow_rate;
-    d.foam_decay_rate = (float)p.foam_decay_rate;
+    d.foam_decay_factor = exp_det_host(-(float)p.foam_decay_rate);
     d.done_target = 0;
     return d;
 }

@@ -22,7 +22,7 @@ struct SpectrumDispatch {
 struct CascadeDispatch {
     int32_t cascade;
     float tile_x, tile_y, depth, time;
-    float whitecap, foam_grow_rate, foam_decay_rate;
+    float whitecap, foam_grow_rate, foam_decay_factor;   // factor = DETMATH exp(-foam_decay_rate), fft_unpack.glsl:62 (uniform per dispatch)
     int32_t done_target;   // persistent kernel: value of done[cascade] once this update's row pass is complete
 };
 
