@@ -189,6 +189,41 @@ __device__ __forceinline__ void sincosf_det(float x, float& s, float& c) {
     s = (q & 2) ? -s0 : s0;
     c = ((q + 1) & 2) ? -c0 : c0;
 }
+// K independent arguments at once: every table constant is fetched once and the K chains advance in lockstep, so the
+// binary64 dependency chains overlap.  Values identical to sincosf_det.
+template <int K>
+__device__ __forceinline__ void sincosf_det_n(const float (&x)[K], float (&s)[K], float (&c)[K]) {
+    double fn[K], r[K], z[K], ps[K], pc[K];
+#pragma unroll
+    for (int e = 0; e < K; ++e) {
+        const double xd = (double)x[e];
+        fn[e] = rint(xd * c_sincos[0]);
+        r[e] = fma(-fn[e], c_sincos[1], xd);
+        r[e] = fma(-fn[e], c_sincos[2], r[e]);
+        z[e] = r[e] * r[e];
+        ps[e] = c_sincos[3];
+        pc[e] = c_sincos[9];
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+#pragma unroll
+        for (int e = 0; e < K; ++e) {
+            ps[e] = fma(ps[e], z[e], c_sincos[4 + j]);
+            pc[e] = fma(pc[e], z[e], c_sincos[10 + j]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < K; ++e) {
+        pc[e] = fma(pc[e], z[e], c_sincos[15]);
+        const float sr = (float)fma(r[e] * z[e], ps[e], r[e]);
+        const float cr = (float)fma(z[e], pc[e], 1.0);
+        const int q = (int)(((long long)fn[e]) & 3);
+        const float s0 = (q & 1) ? cr : sr;
+        const float c0 = (q & 1) ? sr : cr;
+        s[e] = (q & 2) ? -s0 : s0;
+        c[e] = ((q + 1) & 2) ? -c0 : c0;
+    }
+}
 __device__ __forceinline__ float cosf_det(float x) { double s, c; sincos64((double)x, s, c); return (float)c; }
 __device__ __forceinline__ float expf_det(float x) { return (float)exp64((double)x); }
 __device__ __forceinline__ float logf_det(float x) { return (float)log64((double)x); }
