@@ -536,6 +536,8 @@ int ocean_copy_rowpass_to_host(ocean_generator* gen, int cascade, float* host) {
     if (rc) return rc;
     if ((rc = check_cascade(gen, cascade))) return rc;
     if (!host) return fail(OCEAN_ERR_INVALID_ARGUMENT, "host is NULL");
+    // without the taps the column pass drops the scratch lines from L2 once it has consumed them (no DRAM write-back)
+    if (!gen->buf.displacement_f32) return fail(OCEAN_ERR_STATE, "the row-pass scratch is only kept while the taps are on; call ocean_enable_f32_taps(gen, 1) before the update");
     const size_t layer = (size_t)gen->map_size * gen->map_size;
     if (!gen->export_buf) OCEAN_CUDA(dev_alloc(gen, &gen->export_buf, 4 * layer));
     OCEAN_CUDA(ocean::launch_rowpass_export(gen->buf, cascade, gen->export_buf, gen->stream));

@@ -121,7 +121,9 @@ int ocean_copy_spectrum_to_host(ocean_generator* gen, int cascade, float* host);
 
 /* Parity/debug taps (not timed): binary32 maps before the half conversion, the row-pass output
  * ([4][N][N][2] float, == fft_buffer half 1 after the first fft_compute, wave_generator.gd:79) and
- * the twiddle table ([N-1][2] float: stage s, index j at (1<<s)-1+j; fft_butterfly.glsl:27). */
+ * the twiddle table ([N-1][2] float: stage s, index j at (1<<s)-1+j; fft_butterfly.glsl:27).
+ * The row-pass scratch is only preserved while the taps are enabled (otherwise the column pass discards it from
+ * L2 as soon as it is consumed): ocean_copy_rowpass_to_host returns OCEAN_ERR_STATE with the taps off. */
 int ocean_enable_f32_taps(ocean_generator* gen, int enable);
 int ocean_copy_f32_maps_to_host(ocean_generator* gen, int cascade, float* displacement_host, float* normal_host);
 int ocean_copy_rowpass_to_host(ocean_generator* gen, int cascade, float* host);

@@ -273,6 +273,9 @@ def test_error_behaviour():
     with pytest.raises(gow.OceanError):
         g.spectrum_to_host(7)
     g._process(0.0)                                                            # nothing pending: no-op
+    g.update_all(0.02, [gow.WaveCascadeParameters() for _ in range(2)])
+    with pytest.raises(gow.OceanError):
+        g.rowpass_to_host(0)                                                   # the scratch is only kept while the taps are on
     g.free()
 
 
