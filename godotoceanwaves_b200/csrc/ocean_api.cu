@@ -51,6 +51,11 @@ struct ocean_generator {
     ocean::DeviceBuffers buf{};
     float2* twiddles = nullptr;
     float2* export_buf = nullptr;                       // rowpass export scratch (lazy)
+    float2* q_points = nullptr;                         // query staging (lazy, grown on demand): points, outputs, scales
+    float* q_disp = nullptr;
+    float* q_grad = nullptr;
+    float4* q_scales = nullptr;
+    size_t q_capacity = 0;
     ocean::CascadeDispatch* d_cascade = nullptr;        // [num_cascades]
     ocean::SpectrumDispatch* d_spectrum = nullptr;      // [num_cascades]
     ocean::CascadeDispatch* h_cascade = nullptr;        // pinned [kRing][num_cascades]
@@ -102,6 +107,10 @@ void release(ocean_generator* g) {
     cudaFree(g->buf.normal_f32);
     cudaFree(g->twiddles);
     cudaFree(g->export_buf);
+    cudaFree(g->q_points);
+    cudaFree(g->q_disp);
+    cudaFree(g->q_grad);
+    cudaFree(g->q_scales);
     cudaFree(g->d_cascade);
     cudaFree(g->d_spectrum);
     cudaFree(g->d_queue);
@@ -543,6 +552,59 @@ int ocean_copy_rowpass_to_host(ocean_generator* gen, int cascade, float* host) {
     OCEAN_CUDA(ocean::launch_rowpass_export(gen->buf, cascade, gen->export_buf, gen->stream));
     gen->kernel_launches += 1;
     OCEAN_CUDA(cudaMemcpyAsync(host, gen->export_buf, sizeof(float2) * 4 * layer, cudaMemcpyDeviceToHost, gen->stream));
+    OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+    return OCEAN_OK;
+}
+
+// ---- map queries ----
+namespace {
+int upload_scales(ocean_generator* gen, int num_cascades, const float* map_scales_host) {
+    if (num_cascades < 1 || num_cascades > gen->num_cascades)
+        return fail(OCEAN_ERR_INVALID_ARGUMENT, "num_cascades %d outside [1, %d]", num_cascades, gen->num_cascades);
+    if (!map_scales_host) return fail(OCEAN_ERR_INVALID_ARGUMENT, "map_scales is NULL");
+    if (!gen->q_scales) OCEAN_CUDA(dev_alloc(gen, &gen->q_scales, (size_t)gen->num_cascades));
+    OCEAN_CUDA(cudaMemcpyAsync(gen->q_scales, map_scales_host, sizeof(float4) * (size_t)num_cascades, cudaMemcpyHostToDevice, gen->stream));
+    return OCEAN_OK;
+}
+}  // namespace
+
+int ocean_sample_maps_device(ocean_generator* gen, int num_points, const float* points_xz_dev, int num_cascades, const float* map_scales_host,
+                             float* displacement_dev, float* gradient_foam_dev) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    if (num_points < 0) return fail(OCEAN_ERR_INVALID_ARGUMENT, "num_points %d is negative", num_points);
+    if (num_points == 0) return OCEAN_OK;
+    if (!points_xz_dev || !displacement_dev || !gradient_foam_dev) return fail(OCEAN_ERR_INVALID_ARGUMENT, "a device buffer is NULL");
+    if ((rc = upload_scales(gen, num_cascades, map_scales_host))) return rc;
+    OCEAN_CUDA(ocean::launch_sample_maps(gen->buf, num_cascades, reinterpret_cast<const float2*>(points_xz_dev), num_points, gen->q_scales,
+                                         displacement_dev, gradient_foam_dev, gen->stream));
+    gen->kernel_launches += 1;
+    return OCEAN_OK;
+}
+
+int ocean_sample_maps(ocean_generator* gen, int num_points, const float* points_xz_host, int num_cascades, const float* map_scales_host,
+                      float* displacement_host, float* gradient_foam_host) {
+    int rc = check_gen(gen);
+    if (rc) return rc;
+    if (num_points < 0) return fail(OCEAN_ERR_INVALID_ARGUMENT, "num_points %d is negative", num_points);
+    if (num_points == 0) return OCEAN_OK;
+    if (!points_xz_host || !displacement_host || !gradient_foam_host) return fail(OCEAN_ERR_INVALID_ARGUMENT, "a host buffer is NULL");
+    const size_t n = (size_t)num_points;
+    if (n > gen->q_capacity) {
+        OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+        cudaFree(gen->q_points); cudaFree(gen->q_disp); cudaFree(gen->q_grad);
+        gen->q_points = nullptr; gen->q_disp = gen->q_grad = nullptr; gen->q_capacity = 0;
+        OCEAN_CUDA(dev_alloc(gen, &gen->q_points, n));
+        OCEAN_CUDA(dev_alloc(gen, &gen->q_disp, 3 * n));
+        OCEAN_CUDA(dev_alloc(gen, &gen->q_grad, 3 * n));
+        gen->q_capacity = n;
+    }
+    OCEAN_CUDA(cudaMemcpyAsync(gen->q_points, points_xz_host, sizeof(float2) * n, cudaMemcpyHostToDevice, gen->stream));
+    if ((rc = ocean_sample_maps_device(gen, num_points, reinterpret_cast<const float*>(gen->q_points), num_cascades, map_scales_host,
+                                       gen->q_disp, gen->q_grad)))
+        return rc;
+    OCEAN_CUDA(cudaMemcpyAsync(displacement_host, gen->q_disp, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, gen->stream));
+    OCEAN_CUDA(cudaMemcpyAsync(gradient_foam_host, gen->q_grad, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, gen->stream));
     OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
     return OCEAN_OK;
 }

@@ -81,5 +81,8 @@ cudaError_t launch_selftest_math(unsigned long long* failures_dev, unsigned long
 
 // De-interleaves one cascade of the row-pass scratch into [4][N][N][2] floats (debug tap).
 cudaError_t launch_rowpass_export(const DeviceBuffers& b, int cascade, float2* out_dev, cudaStream_t stream);
+// ocean_sample.cu: batched map queries (water.gdshader:27-39,42-84); scales_dev = map_scales[num_cascades] as float4
+cudaError_t launch_sample_maps(const DeviceBuffers& b, int num_cascades, const float2* points_dev, int n, const float4* scales_dev,
+                               float* disp_out_dev, float* grad_out_dev, cudaStream_t stream);
 
 }  // namespace ocean

@@ -174,6 +174,32 @@ class WaveGenerator:
         check(load_library().ocean_copy_rowpass_to_host(self.context, cascade, out.ctypes.data))
         return out
 
+    # -- map queries: the water shader's sampling contract as an op (water.gdshader:27-39,42-84) ----------------
+    @staticmethod
+    def map_scales(parameters) -> np.ndarray:
+        """map_scales[i] = (1/tile_length.x, 1/tile_length.y, displacement_scale, normal_scale), water.gd:102-110
+        (the divisions are float32, as Vector2.ONE / tile_length is in Godot)."""
+        out = np.empty((len(parameters), 4), np.float32)
+        for i, p in enumerate(parameters):
+            out[i, 0] = np.float32(1.0) / np.float32(p.tile_length[0])
+            out[i, 1] = np.float32(1.0) / np.float32(p.tile_length[1])
+            out[i, 2] = p.displacement_scale
+            out[i, 3] = p.normal_scale
+        return out
+
+    def sample(self, points_xz, map_scales) -> tuple:
+        """(displacement [n][3], gradient_foam [n][3]) float32 at world positions points_xz [n][2], summed over the
+        len(map_scales) first cascades: what vertex() and fragment() of water.gdshader read at UV = VERTEX.xz."""
+        self._require()
+        pts = np.ascontiguousarray(points_xz, np.float32).reshape(-1, 2)
+        sc = np.ascontiguousarray(map_scales, np.float32).reshape(-1, 4)
+        n = pts.shape[0]
+        disp = np.empty((n, 3), np.float32)
+        grad = np.empty((n, 3), np.float32)
+        check(load_library().ocean_sample_maps(self.context, n, pts.ctypes.data, sc.shape[0], sc.ctypes.data,
+                                               disp.ctypes.data, grad.ctypes.data))
+        return disp, grad
+
     def twiddles_to_host(self) -> np.ndarray:
         self._require()
         out = np.empty((self.map_size - 1, 2), np.float32)

@@ -119,6 +119,21 @@ int ocean_host_free(void* ptr);
  * [map_size][map_size][4] float = (Re h0(k), Im h0(k), Re h0(-k), -Im h0(-k)) for one cascade. */
 int ocean_copy_spectrum_to_host(ocean_generator* gen, int cascade, float* host);
 
+/* Batched map queries -- the sampling contract of the water shader as an op (what buoyancy / gameplay code needs):
+ *   displacement[p]   = sum_i texture(displacements, vec3(xz*scales_i.xy, i)).xyz * scales_i.z         water.gdshader:27-39
+ *   gradient_foam[p]  = sum_i mix(texture_bicubic(normals, c_i), texture(normals, c_i), min(1, ppm_i*0.1)).xyw
+ *                             * vec3(scales_i.ww, 1),  ppm_i = map_size * min(scales_i.x, scales_i.y)   water.gdshader:42-84
+ * over the first num_cascades layers, map_scales[i] = (1/tile_length.x, 1/tile_length.y, displacement_scale,
+ * normal_scale) as in assets/water/water.gd:102-110.  points_xz: [num_points][2] world x,z (UV = VERTEX.xz);
+ * outputs: [num_points][3] float each.  texture() = exact-weight bilinear filter with REPEAT addressing, binary32,
+ * shader operation order (oracle/sampling.py is the specification).  |xz * scale * map_size| must stay below 2^31.
+ * ocean_sample_maps takes host buffers (copies inside, synchronous); ocean_sample_maps_device takes device pointers for
+ * points and outputs (map_scales stays a host array) and is asynchronous on the generator's stream. */
+int ocean_sample_maps(ocean_generator* gen, int num_points, const float* points_xz_host, int num_cascades, const float* map_scales_host,
+                      float* displacement_host, float* gradient_foam_host);
+int ocean_sample_maps_device(ocean_generator* gen, int num_points, const float* points_xz_dev, int num_cascades, const float* map_scales_host,
+                             float* displacement_dev, float* gradient_foam_dev);
+
 /* Parity/debug taps (not timed): binary32 maps before the half conversion, the row-pass output
  * ([4][N][N][2] float, == fft_buffer half 1 after the first fft_compute, wave_generator.gd:79) and
  * the twiddle table ([N-1][2] float: stage s, index j at (1<<s)-1+j; fft_butterfly.glsl:27).
