@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libocean.so")
 SOURCES = ["ocean_kernels.cu", "ocean_sample.cu", "ocean_api.cu"]
-HEADERS = ["ocean_kernels.cuh", "detmath.cuh", os.path.join("..", "..", "include", "ocean.h")]
+HEADERS = ["ocean_kernels.cuh", "detmath.cuh", "fft_core.cuh", os.path.join("..", "..", "include", "ocean.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -40,16 +40,30 @@ def build_native(force: bool = False, verbose: bool = False, out: str | None = N
     if out is None and not force and not is_stale():
         return LIB_PATH
     target = out or LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", target] + [os.path.join(CSRC, s) for s in SOURCES]
-    if os.path.exists("/usr/bin/g++"):
-        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout)
-    if verbose:
-        print(res.stdout)
+    # several ranks of one job may get here together: one builds (into a temporary file, renamed into place), the others
+    # wait on the lock and then find the library up to date
+    import fcntl
+    with open(target + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if out is None and not force and not is_stale():
+                return LIB_PATH
+            tmp = f"{target}.tmp{os.getpid()}"
+            cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+            if os.path.exists("/usr/bin/g++"):
+                cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout)
+            os.replace(tmp, target)
+            if verbose:
+                print(res.stdout)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return target
 
 
