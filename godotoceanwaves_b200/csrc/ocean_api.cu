@@ -556,6 +556,8 @@ int ocean_copy_rowpass_to_host(ocean_generator* gen, int cascade, float* host) {
     return OCEAN_OK;
 }
 
+float ocean_detmath_expf(float x) { return exp_det_host(x); }
+
 // ---- map queries ----
 namespace {
 int upload_scales(ocean_generator* gen, int num_cascades, const float* map_scales_host) {

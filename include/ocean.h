@@ -119,6 +119,11 @@ int ocean_host_free(void* ptr);
  * [map_size][map_size][4] float = (Re h0(k), Im h0(k), Re h0(-k), -Im h0(-k)) for one cascade. */
 int ocean_copy_spectrum_to_host(ocean_generator* gen, int cascade, float* host);
 
+/* Host evaluation of the DETMATH exp: the library computes exp(-foam_decay_rate), uniform per dispatch
+ * (fft_unpack.glsl:62), on the host with the same binary64 operation sequence the device functions use.  Exported so
+ * that the agreement can be checked without a GPU (tests/test_abi_cpu.py). */
+float ocean_detmath_expf(float x);
+
 /* Batched map queries -- the sampling contract of the water shader as an op (what buoyancy / gameplay code needs):
  *   displacement[p]   = sum_i texture(displacements, vec3(xz*scales_i.xy, i)).xyz * scales_i.z         water.gdshader:27-39
  *   gradient_foam[p]  = sum_i mix(texture_bicubic(normals, c_i), texture(normals, c_i), min(1, ppm_i*0.1)).xyw

@@ -99,3 +99,23 @@ def test_push_constant_mirror_matches_oracle_restatement():
     assert len(gow.RenderingContext.create_push_constant(data)) == 64
     with pytest.raises(AssertionError):
         gow.RenderingContext.create_push_constant([0.0] * 33)
+
+
+def test_host_detmath_exp_matches_the_oracle_bit_for_bit():
+    """exp(-foam_decay_rate) is evaluated inside libocean.so on the HOST (ocean_api.cu: exp_det_host); it must be the very
+    DETMATH function the oracle (and the device code) define -- checked here without a GPU."""
+    import numpy as np
+    lib = gow.load_library()
+    po.set_modes(po.MATH_DET, po.CONTRACT_FMA)
+    ol = po.lib()
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([
+        -np.abs(rng.standard_normal(20000)).astype(np.float32),                 # typical: -delta*(10-foam_amount)*1.15
+        rng.uniform(-120.0, 100.0, 20000).astype(np.float32),                   # across both clamps
+        np.array([0.0, -0.0, 1.0, -1.0, -0.0115, -0.23, -110.0, -110.5, 90.0, 90.5, 1e-30, -1e-30, 88.7, -87.3, -103.9,
+                  np.inf, -np.inf], np.float32)])
+    a = np.array([lib.ocean_detmath_expf(float(x)) for x in xs], np.float32)
+    b = np.array([ol.oracle_expf(float(x)) for x in xs], np.float32)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    n = lib.ocean_detmath_expf(float("nan"))
+    assert n != n
