@@ -56,10 +56,18 @@ struct ocean_generator {
     float* q_grad = nullptr;
     float4* q_scales = nullptr;
     size_t q_capacity = 0;
-    ocean::CascadeDispatch* d_cascade = nullptr;        // [num_cascades]
+    ocean::CascadeDispatch* d_cascade = nullptr;        // [num_cascades] (two-kernel path only)
     ocean::SpectrumDispatch* d_spectrum = nullptr;      // [num_cascades]
+    ocean::TableDispatch* d_tables = nullptr;           // [num_cascades]
     ocean::CascadeDispatch* h_cascade = nullptr;        // pinned [kRing][num_cascades]
     ocean::SpectrumDispatch* h_spectrum = nullptr;      // pinned [kRing][num_cascades]
+    ocean::TableDispatch* h_tables = nullptr;           // pinned [kRing][num_cascades]
+    // dispersion tables are keyed by (tile_length, depth): cascades with equal keys share a slot
+    struct TableKey { float tile_x, tile_y, depth; };
+    std::vector<TableKey> slot_key;                     // [num_cascades] key whose table the slot holds (valid if slot_valid)
+    std::vector<char> slot_valid;
+    std::vector<int> slot_refs;                         // cascades currently pointing at the slot
+    std::vector<int> cascade_slot;                      // [num_cascades] slot of each cascade, -1 = none yet
     cudaEvent_t ring_done[kRing] = {};
     int ring_next = 0;
     cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
@@ -68,7 +76,7 @@ struct ocean_generator {
     bool profiling = false;
     bool prof_valid = false, prof_had_gen = false;
     int* d_queue = nullptr;                             // [1 + num_cascades] work counter + completion counters
-    std::vector<int> done_count;                        // host mirror of the completion counters
+    std::vector<uint32_t> done_count;                   // host mirror of the completion counters (modulo 2^32)
     int resident_ctas = 0;
     std::map<int, std::pair<int*, int>> item_tables;    // cascades per launch -> (device item table, item count)
     bool persistent = true;                             // OCEAN_PIPELINE=split selects the two-kernel path
@@ -81,12 +89,31 @@ struct ocean_generator {
 
 namespace {
 
-int check_gen(ocean_generator* g) {
+// Every entry point runs on the generator's device and hands the caller's current device back on return (a host that
+// drives other CUDA work from the same thread -- a torch process, a C# engine host -- must not find its device changed).
+struct DeviceScope {
+    int prev = -1;
+    ~DeviceScope() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    cudaError_t enter(int device) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) cur = -1;
+        if (cur == device) return cudaSuccess;
+        cudaError_t e = cudaSetDevice(device);
+        if (e == cudaSuccess) prev = cur;
+        return e;
+    }
+};
+int enter_gen(ocean_generator* g, DeviceScope& scope) {
     if (!g) return fail(OCEAN_ERR_INVALID_ARGUMENT, "generator handle is NULL");
-    cudaError_t e = cudaSetDevice(g->device);
+    cudaError_t e = scope.enter(g->device);
     if (e != cudaSuccess) return fail(OCEAN_ERR_CUDA, "cudaSetDevice(%d) failed: %s", g->device, cudaGetErrorString(e));
     return OCEAN_OK;
 }
+#define OCEAN_ENTER(gen)                 \
+    DeviceScope device_scope__;          \
+    int rc = enter_gen(gen, device_scope__)
 
 template <typename T>
 cudaError_t dev_alloc(ocean_generator* g, T** p, size_t count) {
@@ -97,8 +124,13 @@ cudaError_t dev_alloc(ocean_generator* g, T** p, size_t count) {
 
 void release(ocean_generator* g) {
     if (!g) return;
-    cudaSetDevice(g->device);
+    DeviceScope scope;
+    scope.enter(g->device);
     if (g->stream) cudaStreamSynchronize(g->stream);
+    cudaFree(g->buf.disp_table);
+    cudaFree(g->buf.disp_kvy);
+    cudaFree(g->d_tables);
+    if (g->h_tables) cudaFreeHost(g->h_tables);
     cudaFree(g->buf.spectrum);
     cudaFree(g->buf.rowpass);
     cudaFree(g->buf.displacement);
@@ -174,13 +206,12 @@ float exp_det_host(float xf) {
     return (float)(e * scale);
 }
 
-// Push constants of wave_generator.gd:73 (spectrum_modulate) and :85 (fft_unpack).
-ocean::CascadeDispatch make_cascade_dispatch(const ocean_cascade_params& p, int cascade) {
+// Push constants of wave_generator.gd:73 (spectrum_modulate) and :85 (fft_unpack).  tile_length and DEPTH reach the
+// kernels through the dispersion table of `table_slot` (assign_table_slot).
+ocean::CascadeDispatch make_cascade_dispatch(const ocean_cascade_params& p, int cascade, int table_slot) {
     ocean::CascadeDispatch d;
     d.cascade = cascade;
-    d.tile_x = p.tile_length[0];
-    d.tile_y = p.tile_length[1];
-    d.depth = (float)kDepth;
+    d.table_slot = table_slot;
     d.time = (float)p.time;
     d.whitecap = (float)p.whitecap;
     d.foam_grow_rate = (float)p.foam_grow_rate;
@@ -189,40 +220,95 @@ ocean::CascadeDispatch make_cascade_dispatch(const ocean_cascade_params& p, int 
     return d;
 }
 
+// Points cascade `i` at the dispersion table of (tile_length, DEPTH): keeps its slot when the key is unchanged, shares a
+// slot that already holds the key, otherwise claims an unreferenced slot and queues its (re)build in jobs[*n_jobs].
+// There are as many slots as cascades and a cascade holds one reference, so a free slot always exists.
+int assign_table_slot(ocean_generator* g, int i, const ocean_cascade_params& p, ocean::TableDispatch* jobs, int* n_jobs) {
+    const ocean_generator::TableKey key{p.tile_length[0], p.tile_length[1], (float)kDepth};
+    auto same = [&](const ocean_generator::TableKey& k) {
+        return std::memcmp(&k, &key, sizeof key) == 0;       // bit equality: the table is a function of the bits
+    };
+    int cur = g->cascade_slot[i];
+    if (cur >= 0 && g->slot_valid[cur] && same(g->slot_key[cur])) return cur;
+    if (cur >= 0) {
+        g->slot_refs[cur] -= 1;
+        g->cascade_slot[i] = -1;
+    }
+    const int S = (int)g->slot_key.size();
+    int pick = -1;
+    for (int s2 = 0; s2 < S && pick < 0; ++s2)
+        if (g->slot_valid[s2] && same(g->slot_key[s2])) pick = s2;          // shared (or cached) table
+    if (pick < 0) {
+        for (int s2 = 0; s2 < S && pick < 0; ++s2)
+            if (g->slot_refs[s2] == 0) pick = s2;
+        if (pick < 0) return -1;                                            // cannot happen (see above)
+        g->slot_key[pick] = key;
+        g->slot_valid[pick] = 1;
+        ocean::TableDispatch job;
+        job.slot = pick;
+        job.tile_x = key.tile_x;
+        job.tile_y = key.tile_y;
+        job.depth = key.depth;
+        jobs[(*n_jobs)++] = job;
+    }
+    g->slot_refs[pick] += 1;
+    g->cascade_slot[i] = pick;
+    return pick;
+}
+
 // Runs WaveGenerator._update (wave_generator.gd:65-85) for the cascades listed in `indices`
 // (all of them in ONE batched launch sequence; cascades are independent).
 int run_cascades(ocean_generator* g, const int* indices, int n) {
     if (n <= 0) return OCEAN_OK;
     const int slot = g->ring_next;
-    g->ring_next = (g->ring_next + 1) % kRing;
     OCEAN_CUDA(cudaEventSynchronize(g->ring_done[slot]));           // staging slot free again?
     ocean::CascadeDispatch* hc = g->h_cascade + (size_t)slot * g->num_cascades;
     ocean::SpectrumDispatch* hs = g->h_spectrum + (size_t)slot * g->num_cascades;
-    int n_dirty = 0;
-    bool fast_math = true;      // branch-free sqrt/div are valid for sane tile lengths only
+    ocean::TableDispatch* ht = g->h_tables + (size_t)slot * g->num_cascades;
+    int n_dirty = 0, n_tables = 0;
+    const uint32_t per_update = (uint32_t)ocean::a_items_per_cascade(g->map_size);
     for (int k = 0; k < n; ++k) {
         const int i = indices[k];
-        ocean_cascade_params& p = g->pass_parameters[i];
-        for (int a = 0; a < 2; ++a) fast_math = fast_math && p.tile_length[a] >= 1e-6f && p.tile_length[a] <= 1e9f;
-        if (p.should_generate_spectrum) {                            // :68-72
-            hs[n_dirty++] = make_spectrum_dispatch(p, i);
-            p.should_generate_spectrum = 0;
+        const ocean_cascade_params& p = g->pass_parameters[i];
+        if (p.should_generate_spectrum) hs[n_dirty++] = make_spectrum_dispatch(p, i);   // :68-72
+        const int ts = assign_table_slot(g, i, p, ht, &n_tables);
+        if (ts < 0) return fail(OCEAN_ERR_STATE, "no free dispersion-table slot (internal error)");
+        hc[k] = make_cascade_dispatch(p, i, ts);                     // :73,85
+        hc[k].done_target = g->done_count[i] + per_update;           // modulo 2^32
+    }
+    // From here on the device is touched.  The host-side state that must agree with it (dirty flags, the mirror of
+    // the completion counters, the staging ring) is committed only after everything has been enqueued; on a failure
+    // the device counters are re-synchronised from the unchanged mirror so that later launches cannot wait forever.
+    bool counters_touched = false;
+    auto fail_resync = [&](int code) {
+        if (counters_touched) {
+            cudaStreamSynchronize(g->stream);
+            cudaMemcpy(g->d_queue + 1, g->done_count.data(), sizeof(uint32_t) * g->done_count.size(), cudaMemcpyHostToDevice);
         }
-        hc[k] = make_cascade_dispatch(p, i);                         // :73,85
-        g->done_count[i] += ocean::a_items_per_cascade(g->map_size);
-        hc[k].done_target = g->done_count[i];
-    }
-    if (g->profiling) OCEAN_CUDA(cudaEventRecord(g->prof[0], g->stream));
+        return code;
+    };
+#define RUN_CUDA(expr)                                                                                              \
+    do {                                                                                                            \
+        cudaError_t e__ = (expr);                                                                                   \
+        if (e__ != cudaSuccess)                                                                                     \
+            return fail_resync(fail(OCEAN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__)); \
+    } while (0)
+    if (g->profiling) RUN_CUDA(cudaEventRecord(g->prof[0], g->stream));
     if (n_dirty) {
-        OCEAN_CUDA(cudaMemcpyAsync(g->d_spectrum, hs, sizeof(ocean::SpectrumDispatch) * n_dirty, cudaMemcpyHostToDevice, g->stream));
-        OCEAN_CUDA(ocean::launch_spectrum_compute(g->buf, g->d_spectrum, n_dirty, g->stream));
-        g->kernel_launches += 1;
+        RUN_CUDA(cudaMemcpyAsync(g->d_spectrum, hs, sizeof(ocean::SpectrumDispatch) * n_dirty, cudaMemcpyHostToDevice, g->stream));
+        RUN_CUDA(ocean::launch_spectrum_compute(g->buf, g->d_spectrum, n_dirty, g->stream));
     }
-    OCEAN_CUDA(cudaMemcpyAsync(g->d_cascade, hc, sizeof(ocean::CascadeDispatch) * n, cudaMemcpyHostToDevice, g->stream));
-    OCEAN_CUDA(cudaEventRecord(g->ring_done[slot], g->stream));
+    if (n_tables) {
+        RUN_CUDA(cudaMemcpyAsync(g->d_tables, ht, sizeof(ocean::TableDispatch) * n_tables, cudaMemcpyHostToDevice, g->stream));
+        RUN_CUDA(ocean::launch_dispersion_tables(g->buf, g->d_tables, n_tables, g->stream));
+    }
+    const bool two_kernel = !(g->persistent && !g->profiling);
+    if (two_kernel)   // the persistent launch takes its dispatch records by value
+        RUN_CUDA(cudaMemcpyAsync(g->d_cascade, hc, sizeof(ocean::CascadeDispatch) * n, cudaMemcpyHostToDevice, g->stream));
+    RUN_CUDA(cudaEventRecord(g->ring_done[slot], g->stream));
     int launched = 0;
-    if (g->profiling) OCEAN_CUDA(cudaEventRecord(g->prof[1], g->stream));
-    if (g->persistent && !g->profiling) {
+    if (g->profiling) RUN_CUDA(cudaEventRecord(g->prof[1], g->stream));
+    if (!two_kernel) {
         // one persistent launch per <= kMaxPersistentCascades cascades (their dispatch records travel by value)
         for (int first = 0; first < n; first += ocean::kMaxPersistentCascades) {
             const int m = (n - first < ocean::kMaxPersistentCascades) ? n - first : ocean::kMaxPersistentCascades;
@@ -233,28 +319,43 @@ int run_cascades(ocean_generator* g, const int* indices, int n) {
                 std::vector<int> host((size_t)total);
                 ocean::build_item_table(g->map_size, m, group, host.data());
                 int* dev = nullptr;
-                OCEAN_CUDA(dev_alloc(g, &dev, (size_t)total));
-                OCEAN_CUDA(cudaMemcpyAsync(dev, host.data(), sizeof(int) * (size_t)total, cudaMemcpyHostToDevice, g->stream));
-                OCEAN_CUDA(cudaStreamSynchronize(g->stream));          // host vector goes out of scope
+                RUN_CUDA(dev_alloc(g, &dev, (size_t)total));
+                cudaError_t ce = cudaMemcpyAsync(dev, host.data(), sizeof(int) * (size_t)total, cudaMemcpyHostToDevice, g->stream);
+                if (ce == cudaSuccess) ce = cudaStreamSynchronize(g->stream);        // host vector goes out of scope
+                if (ce != cudaSuccess) {
+                    cudaFree(dev);
+                    RUN_CUDA(ce);
+                }
                 it = g->item_tables.emplace(m, std::make_pair(dev, total)).first;
             }
-            OCEAN_CUDA(ocean::launch_cascade_update_persistent(g->buf, hc + first, m, fast_math, g->stream, g->d_queue,
-                                                               it->second.first, it->second.second, g->resident_ctas));
+            counters_touched = true;
+            RUN_CUDA(ocean::launch_cascade_update_persistent(g->buf, hc + first, m, g->stream, g->d_queue, it->second.first,
+                                                             it->second.second, g->resident_ctas));
             launched += 1;
         }
     } else {
-        OCEAN_CUDA(ocean::launch_cascade_update(g->buf, g->d_cascade, n, fast_math, g->stream, &launched, g->profiling ? g->prof[2] : nullptr, g->profiling ? g->prof[4] : nullptr));
-        // keep the device-side completion counters in step with the host mirror (one small copy)
-        OCEAN_CUDA(cudaMemcpyAsync(g->d_queue + 1, g->done_count.data(), sizeof(int) * g->done_count.size(), cudaMemcpyHostToDevice, g->stream));
+        RUN_CUDA(ocean::launch_cascade_update(g->buf, g->d_cascade, n, g->stream, &launched, g->profiling ? g->prof[2] : nullptr,
+                                              g->profiling ? g->prof[4] : nullptr));
+        // (the device-side completion counters are brought in step with the host mirror at the commit below)
     }
     if (g->profiling) {
-        OCEAN_CUDA(cudaEventRecord(g->prof[3], g->stream));
+        RUN_CUDA(cudaEventRecord(g->prof[3], g->stream));
         g->prof_valid = true;
         g->prof_had_gen = n_dirty != 0;
         const int ch = ocean::chunk_cascades(g->map_size);
         g->prof_chunk = n < ch ? n : ch;
     }
-    g->kernel_launches += (uint64_t)launched;
+    // ---- commit ----
+    for (int k = 0; k < n; ++k) {
+        const int i = indices[k];
+        g->pass_parameters[i].should_generate_spectrum = 0;          // :72
+        g->done_count[i] += per_update;
+    }
+    if (two_kernel)
+        RUN_CUDA(cudaMemcpyAsync(g->d_queue + 1, g->done_count.data(), sizeof(uint32_t) * g->done_count.size(), cudaMemcpyHostToDevice, g->stream));
+#undef RUN_CUDA
+    g->ring_next = (g->ring_next + 1) % kRing;
+    g->kernel_launches += (uint64_t)launched + (n_dirty ? 1 : 0) + (n_tables ? 1 : 0);
     g->cascade_updates += (uint64_t)n;
     return OCEAN_OK;
 }
@@ -323,7 +424,8 @@ int ocean_create(int device, int map_size, int num_cascades, ocean_generator** o
     if (e != cudaSuccess || ndev == 0)
         return fail(OCEAN_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return fail(OCEAN_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device, ndev);
-    OCEAN_CUDA(cudaSetDevice(device));
+    DeviceScope device_scope;
+    OCEAN_CUDA(device_scope.enter(device));
     cudaDeviceProp prop;
     OCEAN_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10)
@@ -350,17 +452,25 @@ int ocean_create(int device, int map_size, int num_cascades, ocean_generator** o
     CREATE_CUDA(dev_alloc(g, &g->buf.displacement, C * NN));              // :34
     CREATE_CUDA(dev_alloc(g, &g->buf.normal, C * NN));                    // :35
     CREATE_CUDA(dev_alloc(g, &g->twiddles, (size_t)ocean::kTwiddleCount + 1));   // :32
+    CREATE_CUDA(dev_alloc(g, &g->buf.disp_table, C * (size_t)(map_size / 2 + 1) * map_size));   // one slot per cascade at most
+    CREATE_CUDA(dev_alloc(g, &g->buf.disp_kvy, C * (size_t)map_size));
     CREATE_CUDA(dev_alloc(g, &g->d_cascade, C));
     CREATE_CUDA(dev_alloc(g, &g->d_spectrum, C));
+    CREATE_CUDA(dev_alloc(g, &g->d_tables, C));
     CREATE_CUDA(dev_alloc(g, &g->d_queue, C + 1));
     CREATE_CUDA(cudaMemsetAsync(g->d_queue, 0, sizeof(int) * (C + 1), g->stream));
-    g->done_count.assign(C, 0);
+    g->done_count.assign(C, 0u);
+    g->slot_key.assign(C, ocean_generator::TableKey{0.f, 0.f, 0.f});
+    g->slot_valid.assign(C, 0);
+    g->slot_refs.assign(C, 0);
+    g->cascade_slot.assign(C, -1);
     {
         const char* mode = std::getenv("OCEAN_PIPELINE");
         g->persistent = !(mode && std::strcmp(mode, "split") == 0);
     }
     CREATE_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g->h_cascade), sizeof(ocean::CascadeDispatch) * kRing * C, cudaHostAllocDefault));
     CREATE_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g->h_spectrum), sizeof(ocean::SpectrumDispatch) * kRing * C, cudaHostAllocDefault));
+    CREATE_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g->h_tables), sizeof(ocean::TableDispatch) * kRing * C, cudaHostAllocDefault));
     for (auto& ev : g->ring_done) CREATE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CREATE_CUDA(cudaEventCreate(&g->timer_start));
     CREATE_CUDA(cudaEventCreate(&g->timer_stop));
@@ -391,7 +501,7 @@ int ocean_destroy(ocean_generator* gen) {
 }
 
 int ocean_update(ocean_generator* gen, double delta, ocean_cascade_params* parameters, int count) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     rc = validate_params(gen, parameters, count);
     if (rc) return rc;
@@ -420,7 +530,7 @@ int ocean_update(ocean_generator* gen, double delta, ocean_cascade_params* param
 }
 
 int ocean_process(ocean_generator* gen, ocean_cascade_params* parameters, int count) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     if (gen->pass_num_cascades_remaining == 0) return OCEAN_OK;        // :58
     if (parameters) {
@@ -451,7 +561,7 @@ int ocean_update_all(ocean_generator* gen, double delta, ocean_cascade_params* p
 }
 
 int ocean_get_maps(ocean_generator* gen, void** displacement_dev, void** normal_dev, size_t* layer_bytes) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     if (displacement_dev) *displacement_dev = gen->buf.displacement;
     if (normal_dev) *normal_dev = gen->buf.normal;
@@ -460,7 +570,7 @@ int ocean_get_maps(ocean_generator* gen, void** displacement_dev, void** normal_
 }
 
 int ocean_copy_maps_to_host_async(ocean_generator* gen, int first, int count, void* displacement_host, void* normal_host) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     if (first < 0 || count < 0 || first + count > gen->num_cascades)
         return fail(OCEAN_ERR_INVALID_ARGUMENT, "layer range [%d,%d) outside [0,%d)", first, first + count, gen->num_cascades);
@@ -480,7 +590,7 @@ int ocean_copy_maps_to_host(ocean_generator* gen, int first, int count, void* di
 }
 
 int ocean_synchronize(ocean_generator* gen) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
     return OCEAN_OK;
@@ -497,7 +607,7 @@ int ocean_host_free(void* ptr) {
 }
 
 int ocean_copy_spectrum_to_host(ocean_generator* gen, int cascade, float* host) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     if ((rc = check_cascade(gen, cascade))) return rc;
     if (!host) return fail(OCEAN_ERR_INVALID_ARGUMENT, "host is NULL");
@@ -508,7 +618,7 @@ int ocean_copy_spectrum_to_host(ocean_generator* gen, int cascade, float* host) 
 }
 
 int ocean_enable_f32_taps(ocean_generator* gen, int enable) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
     const size_t n = (size_t)gen->num_cascades * gen->map_size * gen->map_size;
@@ -527,7 +637,7 @@ int ocean_enable_f32_taps(ocean_generator* gen, int enable) {
 }
 
 int ocean_copy_f32_maps_to_host(ocean_generator* gen, int cascade, float* displacement_host, float* normal_host) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     if ((rc = check_cascade(gen, cascade))) return rc;
     if (!gen->buf.displacement_f32) return fail(OCEAN_ERR_STATE, "binary32 taps are disabled; call ocean_enable_f32_taps(gen, 1) first");
@@ -541,7 +651,7 @@ int ocean_copy_f32_maps_to_host(ocean_generator* gen, int cascade, float* displa
 }
 
 int ocean_copy_rowpass_to_host(ocean_generator* gen, int cascade, float* host) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     if ((rc = check_cascade(gen, cascade))) return rc;
     if (!host) return fail(OCEAN_ERR_INVALID_ARGUMENT, "host is NULL");
@@ -572,7 +682,7 @@ int upload_scales(ocean_generator* gen, int num_cascades, const float* map_scale
 
 int ocean_sample_maps_device(ocean_generator* gen, int num_points, const float* points_xz_dev, int num_cascades, const float* map_scales_host,
                              float* displacement_dev, float* gradient_foam_dev) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     if (num_points < 0) return fail(OCEAN_ERR_INVALID_ARGUMENT, "num_points %d is negative", num_points);
     if (num_points == 0) return OCEAN_OK;
@@ -586,7 +696,7 @@ int ocean_sample_maps_device(ocean_generator* gen, int num_points, const float* 
 
 int ocean_sample_maps(ocean_generator* gen, int num_points, const float* points_xz_host, int num_cascades, const float* map_scales_host,
                       float* displacement_host, float* gradient_foam_host) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     if (num_points < 0) return fail(OCEAN_ERR_INVALID_ARGUMENT, "num_points %d is negative", num_points);
     if (num_points == 0) return OCEAN_OK;
@@ -612,7 +722,7 @@ int ocean_sample_maps(ocean_generator* gen, int num_points, const float* points_
 }
 
 int ocean_copy_twiddles_to_host(ocean_generator* gen, float* host) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     if (!host) return fail(OCEAN_ERR_INVALID_ARGUMENT, "host is NULL");
     OCEAN_CUDA(cudaMemcpyAsync(host, gen->twiddles, sizeof(float2) * (gen->map_size - 1), cudaMemcpyDeviceToHost, gen->stream));
@@ -621,7 +731,7 @@ int ocean_copy_twiddles_to_host(ocean_generator* gen, float* host) {
 }
 
 int ocean_get_foam_state(ocean_generator* gen, int cascade, uint16_t* host) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     if ((rc = check_cascade(gen, cascade))) return rc;
     if (!host) return fail(OCEAN_ERR_INVALID_ARGUMENT, "host is NULL");
@@ -633,7 +743,7 @@ int ocean_get_foam_state(ocean_generator* gen, int cascade, uint16_t* host) {
 }
 
 int ocean_set_foam_state(ocean_generator* gen, int cascade, const uint16_t* host) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     if ((rc = check_cascade(gen, cascade))) return rc;
     if (!host) return fail(OCEAN_ERR_INVALID_ARGUMENT, "host is NULL");
@@ -645,14 +755,14 @@ int ocean_set_foam_state(ocean_generator* gen, int cascade, const uint16_t* host
 }
 
 int ocean_timer_start(ocean_generator* gen) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     OCEAN_CUDA(cudaEventRecord(gen->timer_start, gen->stream));
     return OCEAN_OK;
 }
 
 int ocean_timer_stop(ocean_generator* gen, float* elapsed_ms) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     if (!elapsed_ms) return fail(OCEAN_ERR_INVALID_ARGUMENT, "elapsed_ms is NULL");
     OCEAN_CUDA(cudaEventRecord(gen->timer_stop, gen->stream));
@@ -662,7 +772,7 @@ int ocean_timer_stop(ocean_generator* gen, float* elapsed_ms) {
 }
 
 int ocean_set_profiling(ocean_generator* gen, int enable) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     gen->profiling = enable != 0;
     gen->prof_valid = false;
@@ -670,7 +780,7 @@ int ocean_set_profiling(ocean_generator* gen, int enable) {
 }
 
 int ocean_get_last_kernel_times(ocean_generator* gen, float* spectrum_ms, float* rowpass_ms, float* colpass_ms, int* chunk_cascades) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     if (!gen->prof_valid) return fail(OCEAN_ERR_STATE, "no profiled launch yet; call ocean_set_profiling(gen, 1) and run an update");
     OCEAN_CUDA(cudaEventSynchronize(gen->prof[3]));
@@ -683,7 +793,7 @@ int ocean_get_last_kernel_times(ocean_generator* gen, float* spectrum_ms, float*
 }
 
 int ocean_selftest_math(ocean_generator* gen, uint64_t* failures, uint64_t* tested) {
-    int rc = check_gen(gen);
+    OCEAN_ENTER(gen);
     if (rc) return rc;
     if (!failures || !tested) return fail(OCEAN_ERR_INVALID_ARGUMENT, "NULL argument");
     unsigned long long* d = nullptr;

@@ -18,12 +18,21 @@ struct SpectrumDispatch {
     float alpha, peak_frequency, wind_speed, angle, depth, swell, detail, spread;
 };
 
-// Push constants of spectrum_modulate.glsl:24-29 and fft_unpack.glsl:20-25 for one cascade update.
+// Push constants of spectrum_modulate.glsl:24-29 and fft_unpack.glsl:20-25 for one cascade update.  tile_length and
+// depth do not travel per update: everything spectrum_modulate derives from them (k_vec, k_unit, the dispersion
+// relation, :59-61,49) is time-invariant and lives in the dispersion table `table_slot` points at (TableDispatch).
 struct CascadeDispatch {
     int32_t cascade;
-    float tile_x, tile_y, depth, time;
+    int32_t table_slot;
+    float time;
     float whitecap, foam_grow_rate, foam_decay_factor;   // factor = DETMATH exp(-foam_decay_rate), fft_unpack.glsl:62 (uniform per dispatch)
-    int32_t done_target;   // persistent kernel: value of done[cascade] once this update's row pass is complete
+    uint32_t done_target;  // persistent kernel: value of done[cascade] once this update's row pass is complete (wraps)
+};
+
+// One dispersion table to (re)build: spectrum_modulate.glsl:59-61,49 for every wave vector of a tile.
+struct TableDispatch {
+    int32_t slot;
+    float tile_x, tile_y, depth;
 };
 
 struct DeviceBuffers {
@@ -36,6 +45,8 @@ struct DeviceBuffers {
     float4* displacement_f32;  // optional taps (nullptr when disabled)
     float4* normal_f32;
     const float2* twiddles;    // [kTwiddleCount] global copy of the universal twiddle table
+    float4* disp_table;        // [slots][N/2+1][N] (omega, k_vec.x, k_unit.y, k_unit.x) of texel (x, y), y <= N/2
+    float* disp_kvy;           // [slots][N] k_vec.y of row y (first N/2+1 entries used)
     alignas(64) CUtensorMap rowpass_tmap;   // TMA descriptor of `rowpass` (kernel B panel loads)
 };
 
@@ -53,12 +64,15 @@ cudaError_t init_twiddles(float2* twiddles_dev, cudaStream_t stream);
 cudaError_t launch_spectrum_compute(const DeviceBuffers& b, const SpectrumDispatch* dispatch_dev, int count,
                                     cudaStream_t stream);
 
+// Dispersion tables (time-invariant part of spectrum_modulate.glsl: k_vec, k_unit, dispersion_relation) for `count`
+// (tile_length, depth) keys, IEEE-exact operations in the shader's order.
+cudaError_t launch_dispersion_tables(const DeviceBuffers& b, const TableDispatch* jobs_dev, int count, cudaStream_t stream);
+
 // spectrum_modulate + row IFFT (kernel A) and column IFFT + fft_unpack (kernel B) for `count`
-// cascades, issued as L2-sized chunks (chunk_cascades) of one launch pair each.  `fast_math` selects the
-// branch-free correctly-rounded sqrt/div (valid when every tile_length is within [1e-6, 1e9] m).
+// cascades, issued as L2-sized chunks (chunk_cascades) of one launch pair each.
 // Returns the number of kernels launched through *launched.  `mid` / `mid2` (optional) are recorded
 // after kernel A / kernel B of the FIRST chunk (per-kernel timing for bench.py).
-cudaError_t launch_cascade_update(const DeviceBuffers& b, const CascadeDispatch* dispatch_dev, int count, bool fast_math,
+cudaError_t launch_cascade_update(const DeviceBuffers& b, const CascadeDispatch* dispatch_dev, int count,
                                   cudaStream_t stream, int* launched, cudaEvent_t mid = nullptr, cudaEvent_t mid2 = nullptr);
 int chunk_cascades(int map_size);
 
@@ -68,7 +82,7 @@ int chunk_cascades(int map_size);
 // cascade c (monotonic; dispatch[i].done_target is the value to wait for).  item_table_dev/total_items from
 // build_item_table(map_size, count, persistent_group(map_size)); resident_ctas from persistent_grid_size().
 constexpr int kMaxPersistentCascades = 256;
-cudaError_t launch_cascade_update_persistent(const DeviceBuffers& b, const CascadeDispatch* dispatch_host, int count, bool fast_math,
+cudaError_t launch_cascade_update_persistent(const DeviceBuffers& b, const CascadeDispatch* dispatch_host, int count,
                                              cudaStream_t stream, int* queue_dev, const int* item_table_dev, int total_items,
                                              int resident_ctas);
 int build_item_table(int map_size, int count, int group, int* out);

@@ -1,5 +1,5 @@
-"""Committed golden vectors (tests/golden/*.json, written by tools/make_golden.py): the CPU oracle reproduces them here,
-the CUDA path reproduces them on the B200 -- neither side vouches for the other."""
+"""Committed golden vectors (tests/golden/*.json, written by tools/make_golden.py FROM THE REFERENCE'S OWN SHADERS compiled
+for the CPU, oracle/_ref): the C oracle and oracle/_ref reproduce them here, the CUDA path reproduces them on the B200."""
 import glob
 import json
 import os
@@ -60,6 +60,28 @@ def test_oracle_reproduces_golden(path):
                            _scales(params))
     assert _crc(d) == q["displacement_crc"] and _crc(gr) == q["gradient_foam_crc"]
     assert d[:4].tobytes().hex() == q["displacement_head"] and gr[:4].tobytes().hex() == q["gradient_foam_head"]
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_reference_shaders_reproduce_golden(path):
+    """The provenance of the vectors: the compiled reference shaders (prebuilt oracle/_ref on the GPU box) give them."""
+    from oracle import pyoracle as po
+    from oracle import pyref as pr
+    if not pr.available():
+        pytest.skip("oracle/_ref is neither built nor buildable here")
+    g = json.load(open(path))
+    assert g["generator"].startswith("oracle/_ref")
+    N, C = g["N"], g["C"]
+    pr.set_modes(po.MATH_DET, po.CONTRACT_FMA)
+    gen = pr.RefWaveGenerator(N)
+    gen.init_gpu(max(2, C))
+    params = [demo_params(po.CascadeParams, c) for c in range(C)]
+    for f in range(g["frames"]):
+        gen.update_all(1.0 / 50.0, params)
+        assert _crc(gen.displacement_map[:C]) == g["frames_crc"][f]["displacement"], f"displacement map, frame {f}"
+        assert _crc(gen.normal_map[:C]) == g["frames_crc"][f]["normal"], f"normal/foam map, frame {f}"
+    assert _crc(gen.spectrum[:C]) == g["spectrum_crc"]
+    assert _sub(gen.spectrum[:C], g["subsample_step"]) == g["spectrum_sub"]
 
 
 @pytest.mark.gpu

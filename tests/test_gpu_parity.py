@@ -10,7 +10,7 @@ import math
 import numpy as np
 import pytest
 
-from conftest import demo_params
+from conftest import EDGE_CASES, demo_params
 from oracle import pyoracle as po
 
 pytestmark = pytest.mark.gpu
@@ -277,21 +277,6 @@ def test_error_behaviour():
     with pytest.raises(gow.OceanError):
         g.rowpass_to_host(0)                                                   # the scratch is only kept while the taps are on
     g.free()
-
-
-EDGE_CASES = {
-    "anisotropic_tile": dict(tile_length=(93.0, 41.0)),
-    "detail_damped_zeros": dict(detail=0.35, tile_length=(16.0, 16.0)),       # exp(-(1-detail)^2 k^2) underflows to exact 0
-    "wind_negative_dir": dict(wind_direction=-135.0, wind_speed=3.0, fetch_length=2.0),
-    "wind_360": dict(wind_direction=360.0, spread=1.0),
-    "no_spread_swell2": dict(spread=0.0, swell=2.0),
-    "shallow_long_waves": dict(tile_length=(4000.0, 4000.0)),                   # tanh(k*depth) < 1 on most texels
-    "tiny_tile": dict(tile_length=(0.5, 0.5)),
-    "whitecap_high_foam_max": dict(whitecap=1.6, foam_amount=10.0),
-    "seed_wrap": dict(spectrum_seed=(-10000, 2147483600)),                      # uvec2(id + seed) wraps
-    "late_time": dict(time=36000.0),
-    "calm": dict(wind_speed=0.0001, fetch_length=0.0001),
-}
 
 
 @pytest.mark.parametrize("name", sorted(EDGE_CASES))

@@ -1,13 +1,16 @@
-"""Writes tests/golden/*.json: regression anchors for the CPU oracle and the CUDA path.
+"""Writes tests/golden/*.json: golden vectors PRODUCED BY THE REFERENCE'S OWN SHADERS.
 
-The reference itself (GLSL on a Vulkan device + GDScript) cannot run in this image and ships no test vectors
-("parity unpinned"), so these vectors are produced by THIS repository's oracle in its pinned configuration
-(DETMATH + FMA contraction, the mode the CUDA kernels reproduce) after the oracle has passed the SURVEY section-4 pins
-(tests/test_oracle_pins.py) and the independent float64 model cross-check.  They freeze that state: any later change to
-either side that alters a single bit of a spectrum, a map or a query result shows up against them, on the CPU for the
-oracle (-m "not gpu") and on the B200 for the kernels (-m gpu), without one implementation vouching for the other.
+The generator is oracle/pyref.RefWaveGenerator: the six GLSL compute shaders of /root/reference compiled for the CPU
+(oracle/ref/, output oracle/_ref/libocean_ref.so) and sequenced as assets/water/wave_generator.gd sequences them, in
+the numeric-policy configuration the CUDA kernels reproduce (DETMATH transcendentals, FMA contraction of
+x*y +/- z*w -- see oracle/ref/glsl_shim.hpp).  This script therefore only runs where /root/reference is present (this
+container); the vectors travel as small JSON files and are checked
+  * against the C oracle and against oracle/_ref on the CPU (-m "not gpu"),
+  * against the CUDA path on the B200 (-m gpu).
 
 Stored per case: CRC-32 of the full arrays (little-endian bytes) and a strided subsample as hex strings for debugging.
+The map-query vectors are oracle/sampling.py's (the numpy specification of the water shader's
+sampling contract) evaluated on the reference-produced maps.
 
   python tools/make_golden.py            # rewrites tests/golden/
 """
@@ -23,6 +26,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import demo_params          # noqa: E402
 from oracle import pyoracle as po         # noqa: E402
+from oracle import pyref as pr            # noqa: E402
 from oracle import sampling as sp         # noqa: E402
 
 CASES = [dict(name="cfg1_128x1", N=128, C=1, frames=2), dict(name="demo_128x3", N=128, C=3, frames=3),
@@ -47,11 +51,12 @@ def query_points(n, seed):
 
 def run_case(case):
     N, C, frames = case["N"], case["C"], case["frames"]
-    po.set_modes(po.MATH_DET, po.CONTRACT_FMA)
-    gen = po.OracleWaveGenerator(N)
+    pr.set_modes(po.MATH_DET, po.CONTRACT_FMA)
+    gen = pr.RefWaveGenerator(N)
     gen.init_gpu(max(2, C))
     params = [demo_params(po.CascadeParams, c) for c in range(C)]
     out = dict(case)
+    out["generator"] = "oracle/_ref: /root/reference/assets/shaders/compute/*.glsl compiled for the CPU (DETMATH, FMA contraction)"
     out["frames_crc"] = []
     for f in range(frames):
         gen.update_all(1.0 / 50.0, params)
