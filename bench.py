@@ -122,68 +122,162 @@ class ClockSampler:
 _RESULT_OUT = sys.stdout        # replaced in main(): the real stdout, kept apart from library chatter
 
 
-def cpu_arm(map_size: int, cascades: int, steps: int, warmup: int, budget_s=None):
-    """The reference's CPU implementation of the path = the C oracle (oracle/), all host threads.
-    Returns (cascades_per_sec, seconds_per_step, cores, sample description)."""
-    from oracle import pyoracle as po
-    po.set_modes(po.MATH_DET, po.CONTRACT_FMA)
-    params = [synth_params(po.CascadeParams, c) for c in range(cascades)]
-    gen = po.OracleWaveGenerator(map_size)
-    gen.keep_f32 = False
-    for _ in range(max(1, warmup)):          # first step also generates the spectra (not steady state)
-        gen.update_all(1.0 / 50.0, params)
-    # Thread count: all the host threads that actually help.  The OpenMP default (every logical CPU the box shows) can be
-    # far above what the container may use -- 128 spinning threads on a smaller CPU quota ran 100x slower than 64 -- so the
-    # candidates (affinity mask, then halves of it) are timed on two updates each and the fastest is kept.
+def host_threads() -> tuple[int, str]:
+    """Threads the CPU arm uses: one per PHYSICAL core this process may run on (affinity mask, SMT siblings counted
+    once), capped by the cgroup CPU quota when the container has one."""
     try:
-        avail = len(os.sched_getaffinity(0))
+        cpus = sorted(os.sched_getaffinity(0))
     except (AttributeError, OSError):
-        avail = os.cpu_count() or 1
-    best = None
-    for cand in sorted({max(1, avail), max(1, avail // 2), max(1, avail // 4)}, reverse=True):
-        po.lib().oracle_set_num_threads(cand)
-        gen.update_all(1.0 / 50.0, params)
+        cpus = list(range(os.cpu_count() or 1))
+    cores = set()
+    for c in cpus:
+        try:
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
+                cores.add(f.read().strip())
+        except OSError:
+            cores.add(str(c))
+    n = max(1, len(cores))
+    how = f"{n} physical cores of {len(cpus)} logical CPUs in the affinity mask"
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            q = max(1, int(float(quota) / float(period)))
+            if q < n:
+                n, how = q, how + f", capped by the cgroup quota of {q} CPUs"
+    except (OSError, ValueError):
+        pass
+    return n, how
+
+
+def cpu_arm(map_size: int, cascades: int, steps: int, warmup: int, budget_s=None, kind=None):
+    """The reference's CPU implementation of the path on the host cores, on the GPU arm's own workload (`cascades`
+    cascade updates per step).  kind "reference" = oracle/_ref, the reference's six GLSL compute shaders compiled for the
+    CPU (OpenMP over workgroups inside every dispatch); kind "port" = the C oracle, one OpenMP thread per cascade.
+    Every step is timed on its own; the value is cascades / MEDIAN step time after `warmup` untimed steps.
+    Returns a dict for the JSON line."""
+    from oracle import pyoracle as po
+    from oracle import pyref as pr
+    if kind is None:
+        kind = "reference" if pr.available() else "port"
+    threads, how = host_threads()
+    params = [synth_params(po.CascadeParams, c) for c in range(cascades)]
+    if kind == "reference":
+        pr.set_modes(po.MATH_DET, po.CONTRACT_FMA)
+        pr.lib().ref_set_num_threads(threads)
+        gen = pr.RefWaveGenerator(map_size)
+        gen.init_gpu(cascades)
+        step = lambda: gen.update_all(1.0 / 50.0, params)
+        what = "oracle/_ref (the reference's GLSL compute shaders compiled for the CPU, OpenMP over workgroups)"
+    else:
+        po.set_modes(po.MATH_DET, po.CONTRACT_FMA)
+        po.lib().oracle_set_num_threads(threads)
+        gen = po.OracleWaveGenerator(map_size)
+        gen.keep_f32 = False
+        gen.init_gpu(cascades)
+        step = lambda: gen.update_all_batched(1.0 / 50.0, params)
+        what = "C oracle port (oracle/ocean_oracle.c, one OpenMP thread per cascade)"
+    t_begin = time.perf_counter()
+    for _ in range(max(1, warmup)):          # the first step also generates the spectra (not steady state)
+        step()
+    times = []
+    while len(times) < steps:
         t = time.perf_counter()
-        gen.update_all(1.0 / 50.0, params)
-        gen.update_all(1.0 / 50.0, params)
-        t = time.perf_counter() - t
-        if best is None or t < best[0]:
-            best = (t, cand)
-        if t > 1.0 and best[1] != cand:
-            break                                   # already far slower than the best: do not waste the time budget
-    cores = best[1]
-    po.lib().oracle_set_num_threads(cores)
-    t0 = time.perf_counter()
-    done = 0
-    while done < steps:
-        gen.update_all(1.0 / 50.0, params)
-        done += 1
-        if budget_s is not None and time.perf_counter() - t0 >= budget_s:
+        step()
+        times.append(time.perf_counter() - t)
+        if budget_s is not None and len(times) >= 3 and time.perf_counter() - t_begin >= budget_s:
             break
-    dt = time.perf_counter() - t0
-    steps = done
-    sample = f"{steps} steady-state updates of {cascades} cascades at {map_size}x{map_size} (oracle, DETMATH+FMA, OpenMP)"
-    return cascades * steps / dt, dt / steps, cores, sample
+    ts = sorted(times)
+    med = ts[len(ts) // 2]
+    return {"value": cascades / med, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"{len(times)} steady-state steps of {cascades} cascades at {map_size}x{map_size} after {max(1, warmup)} warm-up steps: {what}; "
+                      f"threads = {how}; OMP_PROC_BIND=close OMP_PLACES=cores OMP_WAIT_POLICY=passive",
+            "seconds_per_step": {"median": med, "min": ts[0], "max": ts[-1], "spread": (ts[-1] - ts[0]) / med},
+            "steps": len(times)}
+
+
+def workload_config(args, world: int) -> dict:
+    """The `config` object of both arms (the reference arm runs the same per-GPU workload on the host cores)."""
+    N = args.map_size
+    C = args.sets * args.cascades_per_set
+    return {"workload": f"{N}x{N} x {args.cascades_per_set} cascades, full pipeline incl. foam, {args.sets} independent sets per GPU per step",
+            "map_size": N, "cascades_per_set": args.cascades_per_set, "sets_per_gpu": args.sets,
+            "cascades_per_step_per_gpu": C, "parallelism": f"cascade-sharded x{world}, no data-path collective",
+            "l2": (lambda mib: f"working set {mib:.0f} MiB per step " + ("> 126 MB L2 (inputs larger than L2)" if mib * 2**20 > 126e6
+                                                                         else "fits the 126 MB L2 (NOT an HBM-bound measurement)"))(
+                (ALGO_BYTES_PER_TEXEL + 64) * C * N * N / 2**20)}
 
 
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    # bounded sample of the same workload: one 4-cascade set per step
-    cps, sps, cores, sample = cpu_arm(args.map_size, args.cascades_per_set, args.steps, min(args.warmup, 2))
+    C = args.sets * args.cascades_per_set
+    cb = cpu_arm(args.map_size, C, args.steps, args.warmup, budget_s=args.reference_seconds)
+    cps = cb["value"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": cps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.map_size}x{args.map_size} x {args.cascades_per_set} cascades, full pipeline incl. foam",
-                   "map_size": args.map_size, "cascades_per_step": args.cascades_per_set,
-                   "note": "reference (Godot GLSL on lavapipe) is not runnable in this image; CPU arm = C oracle port"},
+        "impl": "reference", "metric": METRIC, "value": cps, "unit": UNIT, "n_gpus": args.gpus, "steps": cb["steps"],
+        "warmup": args.warmup, "ms_per_step": cb["seconds_per_step"]["median"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
         "mtexels_per_sec": cps * args.map_size * args.map_size / 1e6,
-        "cpu_baseline": {"value": cps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": cb,
         "e2e": {"value": cps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "the reference project itself (Godot + Vulkan/lavapipe) cannot run in this image; its compute shaders can: "
+                "this arm runs them, compiled for the CPU, on the host cores",
     }
     print(json.dumps(line), file=_RESULT_OUT, flush=True)
+
+
+def bind_to_gpu_numa_node(index: int):
+    """Pins this rank to the CPUs next to its GPU (NVML's ideal CPU affinity for the device), so that the pinned host
+    buffers it allocates afterwards are local to the GPU's PCIe root and the ranks do not all land on one memory controller."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = sorted(os.sched_getaffinity(0))
+        return {"bound": True, "cpus_before": before, "cpus_after": len(after), "first_cpu": after[0], "last_cpu": after[-1]}
+    except Exception as e:                       # no NVML / not permitted: run unbound and say so
+        return {"bound": False, "why": str(e)[:120]}
+
+
+def preflight_sharding_check(world: int, local_rank: int, dist):
+    """cascade-sharded over the GPUs of this job == one GPU, bit for bit.  Every rank runs its shard of a small
+    workload through the sharded path and, on its own GPU, the whole workload through a single generator; rank 0 gathers the
+    CRCs.  Costs well under a second; the result travels in the JSON line."""
+    import zlib
+    import numpy as np
+    import godotoceanwaves_b200 as gow
+    from godotoceanwaves_b200.sharding import ShardedWaveGenerator, owned_cascades
+    N, C, frames = 128, 16, 3
+    rank = int(os.environ.get("RANK", "0"))
+    params = [synth_params(gow.WaveCascadeParameters, c) for c in range(C)]
+    sh = ShardedWaveGenerator(N, rank=rank, world=world, device=local_rank)
+    for _ in range(frames):
+        sh.update_all(1.0 / 50.0, params)
+    d, n = sh.local_maps_to_host()
+    mine = {c: (zlib.crc32(d[k].tobytes()), zlib.crc32(n[k].tobytes())) for k, c in enumerate(owned_cascades(C, rank, world))}
+    sh.free()
+    ref_params = [synth_params(gow.WaveCascadeParameters, c) for c in range(C)]
+    ref = gow.WaveGenerator(device=local_rank); ref.map_size = N; ref.init_gpu(C)
+    for _ in range(frames):
+        ref.update_all(1.0 / 50.0, ref_params)
+    rd, rn = ref.maps_to_host()
+    ref.free()
+    ok = all(mine[c] == (zlib.crc32(rd[c].tobytes()), zlib.crc32(rn[c].tobytes())) for c in mine)
+    if world > 1:
+        flags = [None] * world
+        dist.all_gather_object(flags, (ok, len(mine)))
+        ok = all(f[0] for f in flags)
+        covered = sum(f[1] for f in flags)
+    else:
+        covered = len(mine)
+    if not ok or covered != C:
+        raise SystemExit(f"sharding pre-flight FAILED on rank {rank}: sharded maps differ from the single-GPU maps")
+    return {"ok": True, "what": f"{C} cascades of {N}x{N}, {frames} updates: round-robin over {world} GPU(s) == one GPU, CRC-32 of both RGBA16F maps per cascade"}
 
 
 def main():
@@ -195,10 +289,19 @@ def main():
     ap.add_argument("--map-size", type=int, default=256)
     ap.add_argument("--cascades-per-set", type=int, default=4)
     ap.add_argument("--sets", type=int, default=32, help="independent cascade sets resident per GPU")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU-baseline sample budget inside the native arm")
+    ap.add_argument("--reference-seconds", type=float, default=150.0, help="time budget of the whole --impl reference run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4-strong"],
+                    help="cfg2: BASELINE configs[1], weak scaling (default, the driver's contract); cfg4-strong: BASELINE configs[3], "
+                         "1024x1024 x 8 cascades split over the GPUs (8/4/2/1 per GPU), strong scaling")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # the CPU arm's OpenMP runtime: threads pinned to cores, sleeping (not spinning) between parallel regions -- must be in
+    # the environment before the first OpenMP library is loaded
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner at every debug
     # level above NONE), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved stdout.
@@ -242,13 +345,21 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    numa = bind_to_gpu_numa_node(local_rank)              # before any pinned allocation: host buffers land next to the GPU
+    strong = args.workload == "cfg4-strong"
+    if strong:
+        args.map_size, args.cascades_per_set, args.sets = 1024, 8, 1
+        if 8 % world:
+            raise SystemExit("cfg4-strong splits 8 cascades: --gpus must be 1, 2, 4 or 8")
     N = args.map_size
-    C = args.sets * args.cascades_per_set                 # cascades resident on this GPU (weak scaling)
+    total_cascades = (args.sets * args.cascades_per_set) if strong else world * args.sets * args.cascades_per_set
+    C = total_cascades // world                            # cascades resident on this GPU
     texels_per_step = C * N * N
+    sharding_check = preflight_sharding_check(world, local_rank, dist if world > 1 else None)
     # cascade-parallel split: the global batch of world*C cascades is dealt round-robin over the
     # ranks, every rank keeps its C cascades resident; no data-path collective.
     from godotoceanwaves_b200.sharding import ShardedWaveGenerator
-    all_params = [synth_params(gow.WaveCascadeParameters, c) for c in range(world * C)]
+    all_params = [synth_params(gow.WaveCascadeParameters, c) for c in range(total_cascades)]
     shard = ShardedWaveGenerator(N, rank=rank, world=world, device=local_rank)
     shard.update_all(1.0 / 50.0, all_params)      # creates the local generator and the spectra
     gen = shard.gen
@@ -282,7 +393,7 @@ def main():
     barrier()
     launches = gen.info().kernel_launches - launches0
     ms = max_over_ranks(ms)
-    value = world * C * args.steps / (ms * 1e-3)
+    value = total_cascades * args.steps / (ms * 1e-3)
 
     # ---- per-kernel times (CUDA events between the two kernels), averaged over a few steps ----
     gen.set_profiling(True)
@@ -304,24 +415,35 @@ def main():
     gow.native.check(lib.ocean_host_alloc(Ct.byref(hd), map_bytes))
     gow.native.check(lib.ocean_host_alloc(Ct.byref(hn), map_bytes))
     e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(2):
+    hd2, hn2 = Ct.c_void_p(), Ct.c_void_p()
+    gow.native.check(lib.ocean_host_alloc(Ct.byref(hd2), map_bytes))
+    gow.native.check(lib.ocean_host_alloc(Ct.byref(hn2), map_bytes))
+    host = [(hd, hn), (hd2, hn2)]
+    for i in range(2):
         gen.update_all(delta, params)
-        gow.native.check(lib.ocean_copy_maps_to_host(gen.context, 0, C, hd, hn))
+        gow.native.check(lib.ocean_snapshot_maps_to_host_async(gen.context, 0, C, host[i][0], host[i][1]))
+    gow.native.check(lib.ocean_wait_snapshot(gen.context))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    for i in range(e2e_steps):
         gen.update_all(delta, params)                                          # marshals + uploads dispatch records
-        gow.native.check(lib.ocean_copy_maps_to_host_async(gen.context, 0, C, hd, hn))
-        gen.synchronize()                                                      # result is on the host
+        # the maps of this step are snapshotted on the device and cross PCIe on a second stream while the next update runs;
+        # the host buffer they land in was last used two steps ago (the snapshot call waits for the previous hand-off)
+        gow.native.check(lib.ocean_snapshot_maps_to_host_async(gen.context, 0, C, host[i & 1][0], host[i & 1][1]))
+    gow.native.check(lib.ocean_wait_snapshot(gen.context))                      # every step's result is on the host
+    gen.synchronize()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * C * e2e_steps / e2e_s
-    h2d_bytes = C * 32                                                         # one CascadeDispatch record per cascade
+    e2e_value = total_cascades * e2e_steps / e2e_s
+    # host -> device per step: the dispatch records travel BY VALUE as kernel parameters of the one launch (a 256-record table
+    # of 32 B records is always sent whole, plus the queue descriptor and the 128 B tensor map)
+    h2d_bytes = 256 * 32 + 128 + 96
     d2h_bytes = 2 * map_bytes
     probe = np.frombuffer((Ct.c_uint16 * 4).from_address(hd.value), np.float16)
     assert np.all(np.isfinite(probe.astype(np.float32)))
-    gow.native.check(lib.ocean_host_free(hd))
-    gow.native.check(lib.ocean_host_free(hn))
+    for a, b in host:
+        gow.native.check(lib.ocean_host_free(a))
+        gow.native.check(lib.ocean_host_free(b))
     gen.free()
 
     if rank != 0:
@@ -337,12 +459,9 @@ def main():
     achieved = ALGO_BYTES_PER_TEXEL * texels_per_step / step_s / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{N}x{N} x {args.cascades_per_set} cascades, full pipeline incl. foam, {args.sets} independent sets per GPU per step",
-                   "map_size": N, "cascades_per_set": args.cascades_per_set, "sets_per_gpu": args.sets,
-                   "cascades_per_step_per_gpu": C, "parallelism": f"cascade-sharded x{world}, no data-path collective",
-                   "l2": f"working set {(ALGO_BYTES_PER_TEXEL + 64) * texels_per_step / 2**20:.0f} MiB per step > 126 MB L2 (inputs larger than L2)"},
+        "config": workload_config(args, world),
         "mtexels_per_sec": value * N * N / 1e6,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -353,10 +472,13 @@ def main():
                 "ms_per_step": e2e_s * 1e3 / e2e_steps, "steps": e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "sharding_check": sharding_check,
+        "host_binding": numa,
     }
+    if strong:
+        line["config"]["workload"] = f"BASELINE configs[3]: 1024x1024 x 8 cascades batched across {world} GPU(s), {C} per GPU (strong scaling)"
     if world == 1 and not args.no_cpu_baseline:
-        cps, sps, cores, sample = cpu_arm(N, args.cascades_per_set, 100000, 1, budget_s=args.cpu_seconds)
-        line["cpu_baseline"] = {"value": cps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        line["cpu_baseline"] = cpu_arm(N, C, 10, 3, budget_s=args.cpu_seconds)
     print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -6,6 +6,7 @@ the Python host-side mirror of the reference's GDScript interface for that path:
 
   WaveCascadeParameters  <- assets/water/wave_cascade_parameters.gd
   WaveGenerator          <- assets/water/wave_generator.gd
+  Water                  <- assets/water/water.gd (scheduler, start times, map_scales, texture hand-off)
   RenderingContext.create_push_constant <- assets/render_context.gd:122-135
 
 There is no CPU fallback: importing works anywhere, but creating a generator without the
@@ -15,6 +16,7 @@ from .native import OceanError, load_library, native_library_path  # noqa: F401
 from .render_context import RenderingContext  # noqa: F401
 from .wave_cascade_parameters import WaveCascadeParameters  # noqa: F401
 from .wave_generator import DEPTH, G, WaveGenerator  # noqa: F401
+from .water import Water  # noqa: F401
 
-__all__ = ["WaveCascadeParameters", "WaveGenerator", "RenderingContext", "OceanError", "load_library",
+__all__ = ["WaveCascadeParameters", "WaveGenerator", "Water", "RenderingContext", "OceanError", "load_library",
            "native_library_path", "G", "DEPTH"]

@@ -48,6 +48,11 @@ struct ocean_generator {
     int map_size = 0;
     int num_cascades = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;                 // snapshot hand-off: device->host copies that overlap the next update
+    cudaEvent_t snap_ready = nullptr, snap_free = nullptr;
+    uint2* snap_disp = nullptr;                         // [num_cascades][N][N] snapshot of the maps (lazy)
+    uint2* snap_normal = nullptr;
+    bool snap_busy = false;
     ocean::DeviceBuffers buf{};
     float2* twiddles = nullptr;
     float2* export_buf = nullptr;                       // rowpass export scratch (lazy)
@@ -56,6 +61,10 @@ struct ocean_generator {
     float* q_grad = nullptr;
     float4* q_scales = nullptr;
     size_t q_capacity = 0;
+    int* spray_counts = nullptr;                        // spray op scratch: block counts / offsets (+ total), grown on demand
+    int spray_count_capacity = 0;
+    void* spray_records = nullptr;                      // spray op staging for the host entry point
+    size_t spray_record_capacity = 0;
     ocean::CascadeDispatch* d_cascade = nullptr;        // [num_cascades] (two-kernel path only)
     ocean::SpectrumDispatch* d_spectrum = nullptr;      // [num_cascades]
     ocean::TableDispatch* d_tables = nullptr;           // [num_cascades]
@@ -79,6 +88,7 @@ struct ocean_generator {
     std::vector<uint32_t> done_count;                   // host mirror of the completion counters (modulo 2^32)
     int resident_ctas = 0;
     std::map<int, std::pair<int*, int>> item_tables;    // cascades per launch -> (device item table, item count)
+    std::map<std::pair<int, int>, std::pair<int*, int>> frame_tables;   // (cascades, frames per launch) -> same, multi-frame order
     bool persistent = true;                             // OCEAN_PIPELINE=split selects the two-kernel path
     std::vector<ocean_cascade_params> pass_parameters;  // wave_generator.gd:14
     int pass_num_cascades_remaining = 0;                // wave_generator.gd:15
@@ -143,10 +153,18 @@ void release(ocean_generator* g) {
     cudaFree(g->q_disp);
     cudaFree(g->q_grad);
     cudaFree(g->q_scales);
+    cudaFree(g->snap_disp);
+    cudaFree(g->snap_normal);
+    if (g->copy_stream) { cudaStreamSynchronize(g->copy_stream); cudaStreamDestroy(g->copy_stream); }
+    if (g->snap_ready) cudaEventDestroy(g->snap_ready);
+    if (g->snap_free) cudaEventDestroy(g->snap_free);
+    cudaFree(g->spray_counts);
+    cudaFree(g->spray_records);
     cudaFree(g->d_cascade);
     cudaFree(g->d_spectrum);
     cudaFree(g->d_queue);
     for (auto& kv : g->item_tables) cudaFree(kv.second.first);
+    for (auto& kv : g->frame_tables) cudaFree(kv.second.first);
     if (g->h_cascade) cudaFreeHost(g->h_cascade);
     if (g->h_spectrum) cudaFreeHost(g->h_spectrum);
     for (auto& ev : g->ring_done)
@@ -217,6 +235,7 @@ ocean::CascadeDispatch make_cascade_dispatch(const ocean_cascade_params& p, int 
     d.foam_grow_rate = (float)p.foam_grow_rate;
     d.foam_decay_factor = exp_det_host(-(float)p.foam_decay_rate);
     d.done_target = 0;
+    d.wait_target = 0;
     return d;
 }
 
@@ -457,9 +476,9 @@ int ocean_create(int device, int map_size, int num_cascades, ocean_generator** o
     CREATE_CUDA(dev_alloc(g, &g->d_cascade, C));
     CREATE_CUDA(dev_alloc(g, &g->d_spectrum, C));
     CREATE_CUDA(dev_alloc(g, &g->d_tables, C));
-    CREATE_CUDA(dev_alloc(g, &g->d_queue, C + 1));
-    CREATE_CUDA(cudaMemsetAsync(g->d_queue, 0, sizeof(int) * (C + 1), g->stream));
-    g->done_count.assign(C, 0u);
+    CREATE_CUDA(dev_alloc(g, &g->d_queue, 2 * C + 1));
+    CREATE_CUDA(cudaMemsetAsync(g->d_queue, 0, sizeof(int) * (2 * C + 1), g->stream));
+    g->done_count.assign(2 * C, 0u);                  // [0, C): row-pass counters, [C, 2C): column-pass counters
     g->slot_key.assign(C, ocean_generator::TableKey{0.f, 0.f, 0.f});
     g->slot_valid.assign(C, 0);
     g->slot_refs.assign(C, 0);
@@ -560,6 +579,133 @@ int ocean_update_all(ocean_generator* gen, double delta, ocean_cascade_params* p
     return OCEAN_OK;
 }
 
+int ocean_update_frames(ocean_generator* gen, double delta, ocean_cascade_params* parameters, int count, int frames) {
+    OCEAN_ENTER(gen);
+    if (rc) return rc;
+    if (frames < 0) return fail(OCEAN_ERR_INVALID_ARGUMENT, "frames %d is negative", frames);
+    if (frames == 0) return OCEAN_OK;
+    const int per_launch = count > 0 ? ocean::kMaxPersistentCascades / count : 0;
+    if (!gen->persistent || gen->profiling || per_launch < 2) {        // two-kernel path / huge sets: frame by frame
+        for (int f = 0; f < frames; ++f)
+            if ((rc = ocean_update_all(gen, delta, parameters, count))) return rc;
+        return OCEAN_OK;
+    }
+    // frame 0 exactly as ocean_update_all: flush of a pending pass, time/rate advance, spectra and tables where needed
+    if ((rc = ocean_update_all(gen, delta, parameters, count))) return rc;
+    const uint32_t a_per = (uint32_t)ocean::a_items_per_cascade(gen->map_size), b_per = (uint32_t)ocean::b_items_per_cascade(gen->map_size);
+    const int C = gen->num_cascades;
+    std::vector<ocean::CascadeDispatch> rec;
+    int done = 1;
+    while (done < frames) {
+        const int F = (frames - done < per_launch) ? frames - done : per_launch;
+        rec.resize((size_t)F * count);
+        for (int f = 0; f < F; ++f) {
+            for (int i = 0; i < count; ++i) {                              // wave_generator.gd:100-106, once per frame
+                ocean_cascade_params& p = parameters[i];
+                p.time += delta;
+                p.foam_grow_rate = delta * p.foam_amount * 7.5;
+                p.foam_decay_rate = delta * std::fmax(0.5, 10.0 - p.foam_amount) * 1.15;
+                ocean::CascadeDispatch d = make_cascade_dispatch(p, i, gen->cascade_slot[i]);
+                d.done_target = gen->done_count[i] + (uint32_t)(f + 1) * a_per;
+                d.wait_target = gen->done_count[C + i] + (uint32_t)f * b_per;
+                rec[(size_t)f * count + i] = d;
+            }
+        }
+        auto key = std::make_pair(count, F);
+        auto it = gen->frame_tables.find(key);
+        if (it == gen->frame_tables.end()) {
+            const int total = ocean::build_item_table_frames(gen->map_size, count, F, nullptr);
+            std::vector<int> host((size_t)total);
+            ocean::build_item_table_frames(gen->map_size, count, F, host.data());
+            int* dev = nullptr;
+            OCEAN_CUDA(dev_alloc(gen, &dev, (size_t)total));
+            cudaError_t ce = cudaMemcpyAsync(dev, host.data(), sizeof(int) * (size_t)total, cudaMemcpyHostToDevice, gen->stream);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(gen->stream);
+            if (ce != cudaSuccess) {
+                cudaFree(dev);
+                return fail(OCEAN_ERR_CUDA, "item table upload failed: %s", cudaGetErrorString(ce));
+            }
+            it = gen->frame_tables.emplace(key, std::make_pair(dev, total)).first;
+        }
+        cudaError_t le = ocean::launch_cascade_update_persistent(gen->buf, rec.data(), F * count, gen->stream, gen->d_queue, it->second.first,
+                                                                 it->second.second, gen->resident_ctas, true);
+        if (le != cudaSuccess) {
+            cudaStreamSynchronize(gen->stream);
+            cudaMemcpy(gen->d_queue + 1, gen->done_count.data(), sizeof(uint32_t) * gen->done_count.size(), cudaMemcpyHostToDevice);
+            return fail(OCEAN_ERR_CUDA, "multi-frame launch failed: %s", cudaGetErrorString(le));
+        }
+        for (int i = 0; i < count; ++i) {
+            gen->done_count[i] += (uint32_t)F * a_per;
+            gen->done_count[C + i] += (uint32_t)F * b_per;
+        }
+        gen->kernel_launches += 1;
+        gen->cascade_updates += (uint64_t)F * count;
+        done += F;
+    }
+    gen->pass_parameters.assign(parameters, parameters + count);
+    for (int i = 0; i < count; ++i) gen->pass_parameters[i].should_generate_spectrum = 0;
+    gen->pass_num_cascades_remaining = 0;
+    return OCEAN_OK;
+}
+
+// ---- Water node hand-off (assets/water/water.gd) ----
+int ocean_scheduler_init(ocean_scheduler* s, double updates_per_second) {
+    if (!s) return fail(OCEAN_ERR_INVALID_ARGUMENT, "scheduler is NULL");
+    s->updates_per_second = updates_per_second;       // water.gd:51
+    s->time = 0.0;                                    // :62
+    s->next_update_time = 0.0;                        // :63
+    return OCEAN_OK;
+}
+
+int ocean_scheduler_set_rate(ocean_scheduler* s, double value) {                  // water.gd:52-54
+    if (!s) return fail(OCEAN_ERR_INVALID_ARGUMENT, "scheduler is NULL");
+    s->next_update_time = s->next_update_time - (1.0 / (s->updates_per_second + 1e-10) - 1.0 / (value + 1e-10));
+    s->updates_per_second = value;
+    return OCEAN_OK;
+}
+
+int ocean_scheduler_tick(ocean_scheduler* s, double delta, double* update_delta) {   // water.gd:75-82
+    if (!s) {
+        fail(OCEAN_ERR_INVALID_ARGUMENT, "scheduler is NULL");
+        return 0;
+    }
+    int due = 0;
+    if (s->updates_per_second == 0 || s->time >= s->next_update_time) {              // :77
+        const double target_update_delta = 1.0 / (s->updates_per_second + 1e-10);    // :78
+        const double ud = (s->updates_per_second == 0) ? delta : target_update_delta + (s->time - s->next_update_time);   // :79
+        s->next_update_time = s->time + target_update_delta;                         // :80
+        if (update_delta) *update_delta = ud;
+        due = 1;                                                                     // :81 _update_water(update_delta)
+    }
+    s->time += delta;                                                                // :82
+    return due;
+}
+
+int ocean_water_frame(ocean_generator* gen, ocean_scheduler* s, double delta, ocean_cascade_params* parameters, int count, int* did_update) {
+    if (!s) return fail(OCEAN_ERR_INVALID_ARGUMENT, "scheduler is NULL");
+    double ud = 0.0;
+    const int due = ocean_scheduler_tick(s, delta, &ud);
+    if (did_update) *did_update = due;
+    if (due) {                                                                       // Water._process -> _update_water, :112-114
+        const int rc = ocean_update(gen, ud, parameters, count);
+        if (rc) return rc;
+    }
+    return ocean_process(gen, parameters, count);                                    // the child node's _process, wave_generator.gd:56-63
+}
+
+int ocean_map_scales(const ocean_cascade_params* parameters, int count, float* map_scales) {     // water.gd:102-110
+    if (!parameters || !map_scales) return fail(OCEAN_ERR_INVALID_ARGUMENT, "NULL argument");
+    for (int i = 0; i < count; ++i) {
+        map_scales[4 * i + 0] = 1.0f / parameters[i].tile_length[0];     // Vector2.ONE / tile_length (binary32)
+        map_scales[4 * i + 1] = 1.0f / parameters[i].tile_length[1];
+        map_scales[4 * i + 2] = (float)parameters[i].displacement_scale;
+        map_scales[4 * i + 3] = (float)parameters[i].normal_scale;
+    }
+    return OCEAN_OK;
+}
+
+double ocean_water_default_time(int cascade) { return 120.0 + M_PI * cascade; }                   // water.gd:32
+
 int ocean_get_maps(ocean_generator* gen, void** displacement_dev, void** normal_dev, size_t* layer_bytes) {
     OCEAN_ENTER(gen);
     if (rc) return rc;
@@ -579,6 +725,48 @@ int ocean_copy_maps_to_host_async(ocean_generator* gen, int first, int count, vo
         OCEAN_CUDA(cudaMemcpyAsync(displacement_host, gen->buf.displacement + first * layer, sizeof(uint2) * layer * count, cudaMemcpyDeviceToHost, gen->stream));
     if (normal_host)
         OCEAN_CUDA(cudaMemcpyAsync(normal_host, gen->buf.normal + first * layer, sizeof(uint2) * layer * count, cudaMemcpyDeviceToHost, gen->stream));
+    return OCEAN_OK;
+}
+
+int ocean_snapshot_maps_to_host_async(ocean_generator* gen, int first, int count, void* displacement_host, void* normal_host) {
+    OCEAN_ENTER(gen);
+    if (rc) return rc;
+    if (first < 0 || count < 0 || first + count > gen->num_cascades)
+        return fail(OCEAN_ERR_INVALID_ARGUMENT, "layer range [%d,%d) outside [0,%d)", first, first + count, gen->num_cascades);
+    if (count == 0) return OCEAN_OK;
+    const size_t layer = (size_t)gen->map_size * gen->map_size;
+    if (!gen->copy_stream) {
+        OCEAN_CUDA(cudaStreamCreateWithFlags(&gen->copy_stream, cudaStreamNonBlocking));
+        OCEAN_CUDA(cudaEventCreateWithFlags(&gen->snap_ready, cudaEventDisableTiming));
+        OCEAN_CUDA(cudaEventCreateWithFlags(&gen->snap_free, cudaEventDisableTiming));
+        OCEAN_CUDA(dev_alloc(gen, &gen->snap_disp, (size_t)gen->num_cascades * layer));
+        OCEAN_CUDA(dev_alloc(gen, &gen->snap_normal, (size_t)gen->num_cascades * layer));
+    }
+    // the snapshot buffers are free again once the previous hand-off has left the device
+    if (gen->snap_busy) OCEAN_CUDA(cudaStreamWaitEvent(gen->stream, gen->snap_free, 0));
+    if (displacement_host)
+        OCEAN_CUDA(cudaMemcpyAsync(gen->snap_disp + first * layer, gen->buf.displacement + first * layer, sizeof(uint2) * layer * count,
+                                   cudaMemcpyDeviceToDevice, gen->stream));
+    if (normal_host)
+        OCEAN_CUDA(cudaMemcpyAsync(gen->snap_normal + first * layer, gen->buf.normal + first * layer, sizeof(uint2) * layer * count,
+                                   cudaMemcpyDeviceToDevice, gen->stream));
+    OCEAN_CUDA(cudaEventRecord(gen->snap_ready, gen->stream));
+    OCEAN_CUDA(cudaStreamWaitEvent(gen->copy_stream, gen->snap_ready, 0));
+    if (displacement_host)
+        OCEAN_CUDA(cudaMemcpyAsync(displacement_host, gen->snap_disp + first * layer, sizeof(uint2) * layer * count, cudaMemcpyDeviceToHost,
+                                   gen->copy_stream));
+    if (normal_host)
+        OCEAN_CUDA(cudaMemcpyAsync(normal_host, gen->snap_normal + first * layer, sizeof(uint2) * layer * count, cudaMemcpyDeviceToHost,
+                                   gen->copy_stream));
+    OCEAN_CUDA(cudaEventRecord(gen->snap_free, gen->copy_stream));
+    gen->snap_busy = true;
+    return OCEAN_OK;
+}
+
+int ocean_wait_snapshot(ocean_generator* gen) {
+    OCEAN_ENTER(gen);
+    if (rc) return rc;
+    if (gen->copy_stream) OCEAN_CUDA(cudaStreamSynchronize(gen->copy_stream));
     return OCEAN_OK;
 }
 
@@ -718,6 +906,110 @@ int ocean_sample_maps(ocean_generator* gen, int num_points, const float* points_
     OCEAN_CUDA(cudaMemcpyAsync(displacement_host, gen->q_disp, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, gen->stream));
     OCEAN_CUDA(cudaMemcpyAsync(gradient_foam_host, gen->q_grad, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, gen->stream));
     OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+    return OCEAN_OK;
+}
+
+// ---- spray candidates ----
+static_assert(sizeof(ocean_spray_record) == 32, "ocean_spray_record layout");
+
+int ocean_spray_grid(int num_particles, const float* emission_transform, float* points_xz_host) {
+    if (num_particles < 0) return fail(OCEAN_ERR_INVALID_ARGUMENT, "num_particles %d is negative", num_particles);
+    if (num_particles == 0) return OCEAN_OK;
+    if (!points_xz_host) return fail(OCEAN_ERR_INVALID_ARGUMENT, "points_xz is NULL");
+    static const float identity[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    const float* E = emission_transform ? emission_transform : identity;
+    // sea_spray_particle.gdshader:47,52-54, binary32 with every operation rounded on its own (volatile defeats contraction)
+    const unsigned t = (unsigned)std::sqrt((float)num_particles);
+    if (t < 2) return fail(OCEAN_ERR_INVALID_ARGUMENT, "num_particles %d gives a grid side below 2 (division by t - 1)", num_particles);
+    const float tm1 = (float)t - 1.0f;
+    for (unsigned i = 0; i < (unsigned)num_particles; ++i) {
+        volatile float cx = (float)(i / t) / tm1, cz = (float)(i % t) / tm1;
+        cx = cx - 0.5f; cz = cz - 0.5f;
+        cx = cx * 10.0f; cz = cz * 10.0f;
+        for (int k = 0; k < 2; ++k) {
+            const float* row = E + 4 * (k == 0 ? 0 : 2);
+            volatile float a = row[0] * cx, b0 = row[1] * 0.0f, c = row[2] * cz;
+            volatile float sum = a + b0;
+            sum = sum + c;
+            sum = sum + row[3];
+            points_xz_host[2 * (size_t)i + k] = sum;
+        }
+    }
+    return OCEAN_OK;
+}
+
+int ocean_extract_spray_device(ocean_generator* gen, int num_candidates, const float* points_xz_dev, int num_cascades,
+                               const float* map_scales_host, const float* particle_scale, int max_records,
+                               ocean_spray_record* records_dev, int* num_active_dev) {
+    OCEAN_ENTER(gen);
+    if (rc) return rc;
+    if (num_candidates < 0 || max_records < 0) return fail(OCEAN_ERR_INVALID_ARGUMENT, "negative count");
+    if (!num_active_dev) return fail(OCEAN_ERR_INVALID_ARGUMENT, "num_active is NULL");
+    if (num_candidates == 0) {
+        OCEAN_CUDA(cudaMemsetAsync(num_active_dev, 0, sizeof(int), gen->stream));
+        return OCEAN_OK;
+    }
+    if (!points_xz_dev || !particle_scale || (max_records > 0 && !records_dev)) return fail(OCEAN_ERR_INVALID_ARGUMENT, "a buffer is NULL");
+    if ((rc = upload_scales(gen, num_cascades, map_scales_host))) return rc;
+    const int blocks = ocean::spray_blocks(num_candidates);
+    if (blocks + 1 > gen->spray_count_capacity) {
+        OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+        cudaFree(gen->spray_counts);
+        gen->spray_counts = nullptr;
+        gen->spray_count_capacity = 0;
+        OCEAN_CUDA(dev_alloc(gen, &gen->spray_counts, (size_t)blocks + 1));
+        gen->spray_count_capacity = blocks + 1;
+    }
+    OCEAN_CUDA(ocean::launch_extract_spray(gen->buf, num_cascades, reinterpret_cast<const float2*>(points_xz_dev), num_candidates, gen->q_scales,
+                                           make_float3(particle_scale[0], particle_scale[1], particle_scale[2]), gen->spray_counts, records_dev,
+                                           max_records, gen->stream));
+    gen->kernel_launches += 3;
+    OCEAN_CUDA(cudaMemcpyAsync(num_active_dev, gen->spray_counts + blocks, sizeof(int), cudaMemcpyDeviceToDevice, gen->stream));
+    return OCEAN_OK;
+}
+
+int ocean_extract_spray(ocean_generator* gen, int num_candidates, const float* points_xz_host, int num_cascades,
+                        const float* map_scales_host, const float* particle_scale, int max_records,
+                        ocean_spray_record* records_host, int* num_active) {
+    OCEAN_ENTER(gen);
+    if (rc) return rc;
+    if (num_candidates < 0 || max_records < 0) return fail(OCEAN_ERR_INVALID_ARGUMENT, "negative count");
+    if (!num_active) return fail(OCEAN_ERR_INVALID_ARGUMENT, "num_active is NULL");
+    *num_active = 0;
+    if (num_candidates == 0) return OCEAN_OK;
+    if (!points_xz_host || (max_records > 0 && !records_host)) return fail(OCEAN_ERR_INVALID_ARGUMENT, "a host buffer is NULL");
+    const size_t n = (size_t)num_candidates;
+    if (n > gen->q_capacity) {                       // the candidate staging buffer is shared with the map-query op
+        OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+        cudaFree(gen->q_points); cudaFree(gen->q_disp); cudaFree(gen->q_grad);
+        gen->q_points = nullptr; gen->q_disp = gen->q_grad = nullptr; gen->q_capacity = 0;
+        OCEAN_CUDA(dev_alloc(gen, &gen->q_points, n));
+        OCEAN_CUDA(dev_alloc(gen, &gen->q_disp, 3 * n));
+        OCEAN_CUDA(dev_alloc(gen, &gen->q_grad, 3 * n));
+        gen->q_capacity = n;
+    }
+    const size_t rec_bytes = ((size_t)max_records + 1) * sizeof(ocean_spray_record);    // + one slot for the count
+    if (rec_bytes > gen->spray_record_capacity) {
+        OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+        cudaFree(gen->spray_records);
+        gen->spray_records = nullptr;
+        gen->spray_record_capacity = 0;
+        OCEAN_CUDA(cudaMalloc(&gen->spray_records, rec_bytes));
+        gen->device_bytes += rec_bytes;
+        gen->spray_record_capacity = rec_bytes;
+    }
+    ocean_spray_record* recs = static_cast<ocean_spray_record*>(gen->spray_records);
+    int* count_dev = reinterpret_cast<int*>(recs + max_records);
+    OCEAN_CUDA(cudaMemcpyAsync(gen->q_points, points_xz_host, sizeof(float2) * n, cudaMemcpyHostToDevice, gen->stream));
+    if ((rc = ocean_extract_spray_device(gen, num_candidates, reinterpret_cast<const float*>(gen->q_points), num_cascades, map_scales_host,
+                                         particle_scale, max_records, recs, count_dev)))
+        return rc;
+    int count = 0;
+    OCEAN_CUDA(cudaMemcpyAsync(&count, count_dev, sizeof(int), cudaMemcpyDeviceToHost, gen->stream));
+    OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+    const int kept = count < max_records ? count : max_records;
+    if (kept > 0) OCEAN_CUDA(cudaMemcpy(records_host, recs, sizeof(ocean_spray_record) * (size_t)kept, cudaMemcpyDeviceToHost));
+    *num_active = count;
     return OCEAN_OK;
 }
 

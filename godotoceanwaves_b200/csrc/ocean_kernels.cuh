@@ -27,6 +27,8 @@ struct CascadeDispatch {
     float time;
     float whitecap, foam_grow_rate, foam_decay_factor;   // factor = DETMATH exp(-foam_decay_rate), fft_unpack.glsl:62 (uniform per dispatch)
     uint32_t done_target;  // persistent kernel: value of done[cascade] once this update's row pass is complete (wraps)
+    uint32_t wait_target;  // multi-frame launches: value of colpass_done[cascade] once the PREVIOUS frame's column pass of this
+                           // cascade is complete -- its row pass may then overwrite the scratch (0-frame lag: == current value)
 };
 
 // One dispersion table to (re)build: spectrum_modulate.glsl:59-61,49 for every wave vector of a tile.
@@ -82,10 +84,16 @@ int chunk_cascades(int map_size);
 // cascade c (monotonic; dispatch[i].done_target is the value to wait for).  item_table_dev/total_items from
 // build_item_table(map_size, count, persistent_group(map_size)); resident_ctas from persistent_grid_size().
 constexpr int kMaxPersistentCascades = 256;
+// multi_frame: the records describe several consecutive updates of the same cascades (build_item_table_frames): B items then
+// publish their completion in queue_dev[1 + num_cascades + c] and A items wait for wait_target there.
 cudaError_t launch_cascade_update_persistent(const DeviceBuffers& b, const CascadeDispatch* dispatch_host, int count,
                                              cudaStream_t stream, int* queue_dev, const int* item_table_dev, int total_items,
-                                             int resident_ctas);
+                                             int resident_ctas, bool multi_frame = false);
 int build_item_table(int map_size, int count, int group, int* out);
+// Queue order of `frames` consecutive updates of the same `count` cascades in one launch: per frame A(f, c0..) then B(f, c0..);
+// slot of (frame f, cascade position c) = f * count + c.  A(f+1, c) waits for B(f, c) (CascadeDispatch::wait_target).
+int build_item_table_frames(int map_size, int count, int frames, int* out);
+int b_items_per_cascade(int map_size);
 int persistent_group(int map_size);
 cudaError_t persistent_grid_size(int map_size, int* out);
 int a_items_per_cascade(int map_size);
@@ -98,5 +106,11 @@ cudaError_t launch_rowpass_export(const DeviceBuffers& b, int cascade, float2* o
 // ocean_sample.cu: batched map queries (water.gdshader:27-39,42-84); scales_dev = map_scales[num_cascades] as float4
 cudaError_t launch_sample_maps(const DeviceBuffers& b, int num_cascades, const float2* points_dev, int n, const float4* scales_dev,
                                float* disp_out_dev, float* grad_out_dev, cudaStream_t stream);
+
+// ocean_spray.cu: spray candidates (sea_spray_particle.gdshader:80-94) as a stable stream compaction; counts_dev is
+// [spray_blocks(n) + 1] ints of scratch whose last element receives the number of active candidates
+int spray_blocks(int n);
+cudaError_t launch_extract_spray(const DeviceBuffers& b, int num_cascades, const float2* points_dev, int n, const float4* scales_dev,
+                                 float3 particle_scale, int* counts_dev, void* records_dev, int max_records, cudaStream_t stream);
 
 }  // namespace ocean

@@ -24,6 +24,11 @@ class CascadeParamsC(C.Structure):
                 ("time", C.c_double), ("foam_grow_rate", C.c_double), ("foam_decay_rate", C.c_double)]
 
 
+class SchedulerC(C.Structure):
+    """struct ocean_scheduler (include/ocean.h) <- water.gd:51,62-63"""
+    _fields_ = [("updates_per_second", C.c_double), ("time", C.c_double), ("next_update_time", C.c_double)]
+
+
 class InfoC(C.Structure):
     _fields_ = [("device", C.c_int32), ("map_size", C.c_int32), ("num_cascades", C.c_int32),
                 ("pending_cascades", C.c_int32), ("kernel_launches", C.c_uint64),
@@ -40,9 +45,18 @@ SIGNATURES = {
     "ocean_update": (C.c_int, [_H, C.c_double, _P(CascadeParamsC), C.c_int]),
     "ocean_process": (C.c_int, [_H, _P(CascadeParamsC), C.c_int]),
     "ocean_update_all": (C.c_int, [_H, C.c_double, _P(CascadeParamsC), C.c_int]),
+    "ocean_update_frames": (C.c_int, [_H, C.c_double, _P(CascadeParamsC), C.c_int, C.c_int]),
+    "ocean_scheduler_init": (C.c_int, [_P(SchedulerC), C.c_double]),
+    "ocean_scheduler_set_rate": (C.c_int, [_P(SchedulerC), C.c_double]),
+    "ocean_scheduler_tick": (C.c_int, [_P(SchedulerC), C.c_double, _P(C.c_double)]),
+    "ocean_water_frame": (C.c_int, [_H, _P(SchedulerC), C.c_double, _P(CascadeParamsC), C.c_int, _P(C.c_int)]),
+    "ocean_map_scales": (C.c_int, [_P(CascadeParamsC), C.c_int, C.c_void_p]),
+    "ocean_water_default_time": (C.c_double, [C.c_int]),
     "ocean_get_maps": (C.c_int, [_H, _P(C.c_void_p), _P(C.c_void_p), _P(C.c_size_t)]),
     "ocean_copy_maps_to_host": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ocean_copy_maps_to_host_async": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ocean_snapshot_maps_to_host_async": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ocean_wait_snapshot": (C.c_int, [_H]),
     "ocean_synchronize": (C.c_int, [_H]),
     "ocean_host_alloc": (C.c_int, [_P(C.c_void_p), C.c_size_t]),
     "ocean_host_free": (C.c_int, [C.c_void_p]),
@@ -54,6 +68,9 @@ SIGNATURES = {
     "ocean_detmath_expf": (C.c_float, [C.c_float]),
     "ocean_sample_maps": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ocean_sample_maps_device": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ocean_spray_grid": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
+    "ocean_extract_spray": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, _P(C.c_int)]),
+    "ocean_extract_spray_device": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ocean_get_foam_state": (C.c_int, [_H, C.c_int, C.c_void_p]),
     "ocean_set_foam_state": (C.c_int, [_H, C.c_int, C.c_void_p]),
     "ocean_jonswap_alpha": (C.c_double, [C.c_double, C.c_double]),

@@ -74,6 +74,8 @@ class ShardedWaveGenerator:
             self.num_cascades = n
             self.owned = owned_cascades(n, self.rank, self.world)
             self.gen = self._factory(self.map_size, len(self.owned))
+            for i in self.owned:            # a new generator starts with empty spectra (water.gd:84-87 marks them all dirty)
+                parameters[i].should_generate_spectrum = True
         return [parameters[i] for i in self.owned]
 
     # -- WaveGenerator surface (wave_generator.gd:56-63,90-109), restricted to the owned cascades ----------

@@ -24,7 +24,7 @@ def _prop(name, conv):
 
 
 class WaveCascadeParameters:
-    __slots__ = ("_v", "_version")
+    __slots__ = ("_v", "_version", "_synced")
 
     tile_length = _prop("tile_length", lambda v: (float(v[0]), float(v[1])))          # :7
     displacement_scale = _prop("displacement_scale", float)                           # :9
@@ -48,6 +48,7 @@ class WaveCascadeParameters:
                  foam_amount=5.0, spectrum_seed=(0, 0), time=0.0):
         self._v = {}
         self._version = 0
+        self._synced = None                     # the C record that last exchanged the library-mutated fields with this object
         self.spectrum_seed = spectrum_seed
         self.time = time
         self.foam_grow_rate = 0.0
@@ -86,8 +87,10 @@ class WaveCascadeParameters:
         out.foam_decay_rate = v["foam_decay_rate"]
 
     def from_c(self, src: CascadeParamsC) -> None:
-        """Reads back the fields the generator mutates (wave_generator.gd:72,103-106) without
-        touching the version counter."""
+        """Reads back the fields the generator mutates (wave_generator.gd:72,103-106) without touching the version
+        counter; remembers WHICH C record they came from, so that a second generator driving the same object re-marshals
+        it instead of trusting its own stale copy of time / dirty flag."""
+        self._synced = src
         v = self._v
         v["should_generate_spectrum"] = bool(src.should_generate_spectrum)
         v["time"] = src.time

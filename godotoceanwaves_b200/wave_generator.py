@@ -26,6 +26,11 @@ class _Descriptor:
         self.layer_bytes = layer_bytes
 
 
+def _same_record(a, b) -> bool:
+    """ctypes hands out a fresh wrapper object per array access: compare the addresses of the underlying C records."""
+    return C.addressof(a) == C.addressof(b)
+
+
 class WaveGenerator:
     def __init__(self, device: int = 0):
         self.map_size = 0                       # wave_generator.gd:8
@@ -60,7 +65,9 @@ class WaveGenerator:
         seen = self._seen
         for i, p in enumerate(parameters):
             key = (id(p), p._version)
-            if seen[i] != key:                  # untouched objects are already current in the C array
+            # untouched objects are already current in the C array -- provided the library-mutated fields (time, dirty
+            # flag) were last exchanged with THIS record and not with another generator's
+            if seen[i] != key or (p._synced is not None and not _same_record(p._synced, self._carr[i])):
                 p.to_c(self._carr[i])
                 seen[i] = key
         return self._carr
@@ -78,10 +85,17 @@ class WaveGenerator:
         self._readback(self.pass_parameters)
 
     # ---- wave_generator.gd:90-109
-    def update(self, delta: float, parameters) -> None:
-        assert len(parameters) != 0
+    def _auto_init(self, parameters) -> None:
+        """wave_generator.gd:92-93 creates the resources on the first update; a NEW generator has empty spectrum textures,
+        so every cascade must regenerate (what water.gd:84-87 does when it sets the generator up)."""
         if not self.context:
             self.init_gpu(max(2, len(parameters)))
+            for p in parameters:
+                p.should_generate_spectrum = True
+
+    def update(self, delta: float, parameters) -> None:
+        assert len(parameters) != 0
+        self._auto_init(parameters)
         arr = self._marshal(parameters)
         check(load_library().ocean_update(self.context, float(delta), arr, len(parameters)))
         self._readback(parameters)
@@ -90,10 +104,19 @@ class WaveGenerator:
     def update_all(self, delta: float, parameters) -> None:
         """update() + every pending cascade in one batched launch (the throughput path)."""
         assert len(parameters) != 0
-        if not self.context:
-            self.init_gpu(max(2, len(parameters)))
+        self._auto_init(parameters)
         arr = self._marshal(parameters)
         check(load_library().ocean_update_all(self.context, float(delta), arr, len(parameters)))
+        self._readback(parameters)
+        self.pass_parameters = parameters
+
+    def update_frames(self, delta: float, parameters, frames: int) -> None:
+        """`frames` consecutive update_all(delta) calls fused into a few launches (ocean_update_frames): bit-identical
+        results, without the per-frame launch and host latency."""
+        assert len(parameters) != 0
+        self._auto_init(parameters)
+        arr = self._marshal(parameters)
+        check(load_library().ocean_update_frames(self.context, float(delta), arr, len(parameters), int(frames)))
         self._readback(parameters)
         self.pass_parameters = parameters
 
@@ -199,6 +222,33 @@ class WaveGenerator:
         check(load_library().ocean_sample_maps(self.context, n, pts.ctypes.data, sc.shape[0], sc.ctypes.data,
                                                disp.ctypes.data, grad.ctypes.data))
         return disp, grad
+
+    # -- spray candidates: the spawn test of sea_spray_particle.gdshader:80-94 as a stream compaction --------------
+    SPRAY_RECORD = np.dtype([("index", np.uint32), ("start_x", np.float32), ("start_z", np.float32), ("scale_factor", np.float32),
+                             ("particle_scale", np.float32, 3), ("foam", np.float32)])     # struct ocean_spray_record
+
+    @staticmethod
+    def spray_grid(num_particles: int, emission_transform=None) -> np.ndarray:
+        """START_POS.xz of the emitter's particle grid (sea_spray_particle.gdshader:47,52-54), float32 [num_particles][2]."""
+        out = np.empty((num_particles, 2), np.float32)
+        et = None if emission_transform is None else np.ascontiguousarray(emission_transform, np.float32).reshape(12)
+        check(load_library().ocean_spray_grid(num_particles, None if et is None else et.ctypes.data, out.ctypes.data))
+        return out
+
+    def extract_spray(self, points_xz, map_scales, particle_scale=(1.0, 1.0, 1.0), max_records: int | None = None):
+        """The ACTIVE spray candidates among points_xz [n][2] as SPRAY_RECORD rows in candidate order, and their total
+        number (which exceeds len(records) when max_records cut the output)."""
+        self._require()
+        pts = np.ascontiguousarray(points_xz, np.float32).reshape(-1, 2)
+        sc = np.ascontiguousarray(map_scales, np.float32).reshape(-1, 4)
+        ps = np.ascontiguousarray(particle_scale, np.float32).reshape(3)
+        n = pts.shape[0]
+        cap = n if max_records is None else int(max_records)
+        recs = np.zeros(cap, self.SPRAY_RECORD)
+        count = C.c_int(0)
+        check(load_library().ocean_extract_spray(self.context, n, pts.ctypes.data, sc.shape[0], sc.ctypes.data, ps.ctypes.data, cap,
+                                                 recs.ctypes.data, C.byref(count)))
+        return recs[:min(count.value, cap)], count.value
 
     def twiddles_to_host(self) -> np.ndarray:
         self._require()

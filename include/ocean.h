@@ -99,6 +99,35 @@ int ocean_process(ocean_generator* gen, ocean_cascade_params* parameters, int co
  * wave_generator.gd:96-97). */
 int ocean_update_all(ocean_generator* gen, double delta, ocean_cascade_params* parameters, int count);
 
+/* `frames` consecutive ocean_update_all(delta) calls of the same resident cascades, fused: after the first frame the
+ * remaining ones run `256 / count` frames per launch, chained on the device through per-cascade completion counters (the row
+ * pass of frame f+1 waits for the column pass of frame f of the same cascade; the times are accumulated on the host in
+ * binary64, one addition per frame, exactly as wave_generator.gd:103 does).  Results are bit-identical to the frame-by-frame
+ * calls; what it removes is the per-frame launch and host latency (1000-frame foam accumulate/decay loop). */
+int ocean_update_frames(ocean_generator* gen, double delta, ocean_cascade_params* parameters, int count, int frames);
+
+/* ---- the Water node's side of the hand-off (assets/water/water.gd), for hosts that do not bring their own ----
+ * ocean_scheduler: the fixed-rate update accumulator of water.gd:51-54,62-63,75-82 as a POD state machine (binary64, the
+ * arithmetic of the GDScript).  ocean_scheduler_tick(delta) is Water._process(delta) without the generator call: it returns 1
+ * when an update is due and writes the delta to pass to WaveGenerator.update (target period + overshoot, or the frame delta
+ * when updates_per_second == 0), then advances the clock.  ocean_scheduler_set_rate is the updates_per_second setter (:52-54).
+ * ocean_water_frame is one rendered frame of the node pair: Water._process (tick, ocean_update when due) followed by the child
+ * WaveGenerator._process (ocean_process: one pending cascade).  ocean_map_scales fills map_scales[i] = (1 / tile_length.xy,
+ * displacement_scale, normal_scale) (water.gd:102-110; the quotients are binary32 as Vector2.ONE / tile_length is).
+ * ocean_water_default_time(i) = 120.0 + PI * i, the cascade start time of water.gd:32. */
+typedef struct ocean_scheduler {
+    double updates_per_second;   /* water.gd:51, default 50 */
+    double time;                 /* :62 */
+    double next_update_time;     /* :63 */
+} ocean_scheduler;
+int ocean_scheduler_init(ocean_scheduler* s, double updates_per_second);
+int ocean_scheduler_set_rate(ocean_scheduler* s, double updates_per_second);
+int ocean_scheduler_tick(ocean_scheduler* s, double delta, double* update_delta);
+int ocean_water_frame(ocean_generator* gen, ocean_scheduler* s, double delta, ocean_cascade_params* parameters, int count,
+                      int* did_update);
+int ocean_map_scales(const ocean_cascade_params* parameters, int count, float* map_scales /* [count][4] */);
+double ocean_water_default_time(int cascade);
+
 /* descriptors[&'displacement_map'].rid / descriptors[&'normal_map'].rid, wave_generator.gd:34-35,
  * water.gd:95-96.  Device pointers to [num_cascades][map_size][map_size][4] IEEE half (RGBA16F),
  * layer-major, tightly packed: displacement = (hx,hy,hz,0), normal = (dy/dx/(1+|dxx|),
@@ -111,6 +140,12 @@ int ocean_get_maps(ocean_generator* gen, void** displacement_dev, void** normal_
  * stream (use pinned memory from ocean_host_alloc and ocean_synchronize). */
 int ocean_copy_maps_to_host(ocean_generator* gen, int first, int count, void* displacement_host, void* normal_host);
 int ocean_copy_maps_to_host_async(ocean_generator* gen, int first, int count, void* displacement_host, void* normal_host);
+/* Overlapped hand-off: snapshots the layers on the device (one device-to-device copy on the generator's stream) and moves the
+ * snapshot to (pinned) host memory on a second stream, so the NEXT update runs while the maps of this one cross PCIe.
+ * ocean_wait_snapshot() returns when the most recent snapshot has arrived; a new snapshot waits for the previous one to have left
+ * the device.  Use two host buffers alternately. */
+int ocean_snapshot_maps_to_host_async(ocean_generator* gen, int first, int count, void* displacement_host, void* normal_host);
+int ocean_wait_snapshot(ocean_generator* gen);
 int ocean_synchronize(ocean_generator* gen);
 int ocean_host_alloc(void** ptr, size_t bytes); /* pinned host memory */
 int ocean_host_free(void* ptr);
@@ -138,6 +173,33 @@ int ocean_sample_maps(ocean_generator* gen, int num_points, const float* points_
                       float* displacement_host, float* gradient_foam_host);
 int ocean_sample_maps_device(ocean_generator* gen, int num_points, const float* points_xz_dev, int num_cascades, const float* map_scales_host,
                              float* displacement_dev, float* gradient_foam_dev);
+
+/* Spray candidates -- the spawn test of the sea-spray particle shader as a stream-compaction op
+ * (assets/shaders/spatial/sea_spray_particle.gdshader:80-94; the reference evaluates it for every particle of the emitter and
+ * culls the inactive ones, README.md:29).  For each candidate START_POS.xz:
+ *   gradient = sum_i texture(normals, vec3(xz * map_scales[i].xy, i)).xyw;  normal = normalize(vec3(-gradient.x, 1, -gradient.y));
+ *   foam = gradient.z;  normal_factor = mix(.25, 1, min((normal.y - .92) / (.99 - .92), 1));  foam_factor likewise on [.9, 1];
+ *   ACTIVE = normal_factor in [0, 1] && foam > .9;  SCALE_FACTOR = normal_factor * foam_factor;
+ *   PARTICLE_SCALE = vec3(foam_factor * (1 + 1e-3)) * vec3(1, normal_factor, 1) * particle_scale
+ * Only the ACTIVE candidates are returned, in candidate order (stable compaction, deterministic).  *num_active receives their
+ * number even when it exceeds max_records (records beyond max_records are dropped).  oracle/spray.py is the specification.
+ * ocean_spray_grid fills the start positions of the emitter's particle grid (sea_spray_particle.gdshader:47,52-54):
+ * emission_transform = 3 x 4 row-major (basis columns, origin), NULL = identity; points_xz_host: [num_particles][2]. */
+typedef struct ocean_spray_record {
+    uint32_t index;            /* candidate (particle INDEX) */
+    float start_x, start_z;    /* START_POS.xz */
+    float scale_factor;        /* SCALE_FACTOR (:90) */
+    float particle_scale[3];   /* PARTICLE_SCALE (:92-94) */
+    float foam;                /* summed normal_map.a at the start position */
+} ocean_spray_record;
+int ocean_spray_grid(int num_particles, const float* emission_transform, float* points_xz_host);
+int ocean_extract_spray(ocean_generator* gen, int num_candidates, const float* points_xz_host, int num_cascades,
+                        const float* map_scales_host, const float* particle_scale, int max_records,
+                        ocean_spray_record* records_host, int* num_active);
+/* device pointers for the candidates, the records and the count (asynchronous on the generator's stream) */
+int ocean_extract_spray_device(ocean_generator* gen, int num_candidates, const float* points_xz_dev, int num_cascades,
+                               const float* map_scales_host, const float* particle_scale, int max_records,
+                               ocean_spray_record* records_dev, int* num_active_dev);
 
 /* Parity/debug taps (not timed): binary32 maps before the half conversion, the row-pass output
  * ([4][N][N][2] float, == fft_buffer half 1 after the first fft_compute, wave_generator.gd:79) and

@@ -424,3 +424,21 @@ void oracle_cascade_update(float *spectrum, float *fft_buffer, const float *butt
     oracle_fft_compute(butterfly, fft_buffer, map_size);                              /* :82 */
     oracle_fft_unpack(fft_buffer, displacement, normal, disp_f32, normal_f32, map_size, pc_unpack); /* :85 */
 }
+
+/* =====================================================================
+ * A batch of independent cascade updates, one OpenMP thread per cascade (the loops inside the stages then run
+ * serially: nested parallelism is off).  Same arithmetic as `count` calls of oracle_cascade_update; used by the CPU
+ * baseline of bench.py, where a step is many cascades (wave_generator.gd:96-97: cascades are independent).
+ * Layer c of every array belongs to cascade c.
+ * ===================================================================== */
+void oracle_cascade_update_batch(float *spectrum, float *fft_buffer, const float *butterfly,
+                                 uint16_t *displacement, uint16_t *normal, int map_size, int count,
+                                 const int *generate_spectrum, const pc_spectrum_compute *pc_gen,
+                                 const pc_spectrum_modulate *pc_mod, const pc_fft_unpack *pc_unpack) {
+    const size_t NN = (size_t)map_size * map_size;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int c = 0; c < count; ++c)
+        oracle_cascade_update(spectrum + (size_t)c * NN * 4, fft_buffer + (size_t)c * NN * 16, butterfly,
+                              displacement + (size_t)c * NN * 4, normal + (size_t)c * NN * 4, NULL, NULL, map_size,
+                              generate_spectrum[c], &pc_gen[c], &pc_mod[c], &pc_unpack[c]);
+}

@@ -92,6 +92,9 @@ def lib() -> C.CDLL:
         L.oracle_cascade_update.argtypes = [fp, fp, fp, hp, hp, fp, fp, C.c_int, C.c_int,
                                             C.POINTER(PcSpectrumCompute), C.POINTER(PcSpectrumModulate),
                                             C.POINTER(PcFftUnpack)]
+        L.oracle_cascade_update_batch.argtypes = [fp, fp, fp, hp, hp, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                                  C.POINTER(PcSpectrumCompute), C.POINTER(PcSpectrumModulate),
+                                                  C.POINTER(PcFftUnpack)]
         _lib = L
     return _lib
 
@@ -226,7 +229,8 @@ class OracleWaveGenerator:
         i = cascade_index
         lib().oracle_cascade_update(_fp(self.spectrum[i]), _fp(self.fft_buffer[i]), _fp(self.butterfly),
                                     _hp(self.displacement_map[i]), _hp(self.normal_map[i]),
-                                    _fp(self.displacement_f32[i]), _fp(self.normal_f32[i]),
+                                    _fp(self.displacement_f32[i]) if self.keep_f32 else None,
+                                    _fp(self.normal_f32[i]) if self.keep_f32 else None,
                                     self.map_size, int(gen), C.byref(pcg), C.byref(pcm), C.byref(pcu))
 
     # wave_generator.gd:56-63
@@ -256,6 +260,27 @@ class OracleWaveGenerator:
         self.update(delta, parameters)
         while self.pass_num_cascades_remaining:
             self.process()
+
+    def update_all_batched(self, delta: float, parameters) -> None:
+        """Same result as update_all, with the pending cascades run as ONE batch, one OpenMP thread per cascade
+        (oracle_cascade_update_batch) -- the CPU baseline's way of using every host core on a many-cascade step."""
+        self.update(delta, parameters)
+        n = self.pass_num_cascades_remaining
+        assert n == len(parameters) == self.num_cascades or n <= self.num_cascades
+        gen = (C.c_int * n)()
+        pcg = (PcSpectrumCompute * n)()
+        pcm = (PcSpectrumModulate * n)()
+        pcu = (PcFftUnpack * n)()
+        for i in range(n):
+            p = self.pass_parameters[i]
+            gen[i] = int(bool(p.should_generate_spectrum))
+            pcg[i] = pc_spectrum_compute(p, i)
+            p.should_generate_spectrum = False
+            pcm[i] = pc_spectrum_modulate(p, i)
+            pcu[i] = pc_fft_unpack(p, i)
+        lib().oracle_cascade_update_batch(_fp(self.spectrum), _fp(self.fft_buffer), _fp(self.butterfly), _hp(self.displacement_map),
+                                          _hp(self.normal_map), self.map_size, n, gen, pcg, pcm, pcu)
+        self.pass_num_cascades_remaining = 0
 
     # convenience views
     def displacement_half(self) -> np.ndarray:

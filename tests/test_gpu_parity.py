@@ -316,3 +316,44 @@ def test_multi_gpu_sharded_equals_single_gpu():
     res = subprocess.run(cmd, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                          text=True, timeout=600)
     assert res.returncode == 0 and "SHARDING_GPU_OK" in res.stdout, res.stdout[-3000:]
+
+
+@pytest.mark.parametrize("group", ["1", "2"])
+def test_interleaved_queue_groups_against_oracle(group, monkeypatch):
+    """The persistent kernel's work queue runs A(g+1) items between A(g) and B(g): with one or two cascades per group and
+    seven cascades every hand-over of the landing buffer (A -> B, B -> B with a pre-issued panel, B -> A) occurs; all
+    textures must still equal the oracle's bit for bit over three updates."""
+    gow = _gpu()
+    monkeypatch.setenv("OCEAN_QUEUE_GROUP", group)
+    N, C = 128, 7
+    pg, pcpu = _pair(gow.WaveCascadeParameters, C)
+    g = gow.WaveGenerator(); g.map_size = N; g.init_gpu(C)
+    o = po.OracleWaveGenerator(N)
+    o.keep_f32 = False
+    for _ in range(3):
+        g.update_all(0.02, pg)
+        o.update_all(0.02, pcpu)
+    d16, n16 = g.maps_to_host(0, C)
+    assert _bits_equal(d16.view(np.uint16), o.displacement_map[:C]) and _bits_equal(n16.view(np.uint16), o.normal_map[:C])
+    g.free()
+
+
+def test_more_cascades_than_one_launch_holds():
+    """260 cascades of 128x128 = two persistent launches per update (256-record dispatch table); a handful of cascades from
+    both launches are compared with the oracle."""
+    gow = _gpu()
+    N, C = 128, 260
+    pg = [demo_params(gow.WaveCascadeParameters, c) for c in range(C)]
+    g = gow.WaveGenerator(); g.map_size = N; g.init_gpu(C)
+    pick = [0, 1, 129, 255, 256, 259]
+    pcpu = [demo_params(po.CascadeParams, c) for c in pick]
+    o = po.OracleWaveGenerator(N)
+    o.keep_f32 = False
+    for _ in range(2):
+        g.update_all(0.02, pg)
+        o.update_all(0.02, pcpu)
+    d16, n16 = g.maps_to_host(0, C)
+    for k, c in enumerate(pick):
+        assert _bits_equal(d16[c].view(np.uint16), o.displacement_map[k]), c
+        assert _bits_equal(n16[c].view(np.uint16), o.normal_map[k]), c
+    g.free()
