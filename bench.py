@@ -464,7 +464,9 @@ def main():
         "config": workload_config(args, world),
         "mtexels_per_sec": value * N * N / 1e6,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "traffic_kind": "static: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture, not measured in this run",
+                     "peak_source": peak_src,
                      "kernel": "k_update_persistent (one launch per step: time propagation + row IFFT items and column IFFT + map items)",
                      "algorithmic_bytes_per_step": ALGO_BYTES_PER_TEXEL * texels_per_step,
                      "kernel_ms": {"k_modulate_rowfft": ka, "k_colfft_unpack": kb, "cascades_per_launch": kchunk}},

@@ -133,11 +133,12 @@ __device__ __forceinline__ double tanh64(double a) {
     return (a < 0.0) ? -r : r;
 }
 
+// atan(i/8), i = 0..8 (constant memory: a local array would live on the thread's stack)
+__constant__ double c_atan_tab[9] = {
+    0x0.0p+0, 0x1.fd5ba9aac2f6ep-4, 0x1.f5b75f92c80ddp-3, 0x1.6f61941e4def1p-2,
+    0x1.dac670561bb4fp-2, 0x1.1e00babdefeb4p-1, 0x1.4978fa3269ee1p-1,
+    0x1.700a7c5784634p-1, 0x1.921fb54442d18p-1 };
 __device__ __forceinline__ double atan2_64(double y, double x) {   // atan2(0,0) := 0
-    const double ATAN_TAB[9] = {
-        0x0.0p+0, 0x1.fd5ba9aac2f6ep-4, 0x1.f5b75f92c80ddp-3, 0x1.6f61941e4def1p-2,
-        0x1.dac670561bb4fp-2, 0x1.1e00babdefeb4p-1, 0x1.4978fa3269ee1p-1,
-        0x1.700a7c5784634p-1, 0x1.921fb54442d18p-1 };
     const double ax = fabs(x), ay = fabs(y);
     if (ax == 0.0 && ay == 0.0) return 0.0;
     const bool swap = ay > ax;
@@ -153,7 +154,7 @@ __device__ __forceinline__ double atan2_64(double y, double x) {   // atan2(0,0)
     p = fma(p, z, -0x1.2492492492492p-3);
     p = fma(p, z, 0x1.999999999999ap-3);
     p = fma(p, z, -0x1.5555555555555p-2);
-    double r = fma(u * z, p, u) + ATAN_TAB[(int)fi];
+    double r = fma(u * z, p, u) + c_atan_tab[(int)fi];
     if (swap) r = 0x1.921fb54442d18p+0 - r;
     if (x < 0.0) r = 0x1.921fb54442d18p+1 - r;
     return (y < 0.0) ? -r : r;

@@ -805,6 +805,26 @@ int ocean_copy_spectrum_to_host(ocean_generator* gen, int cascade, float* host) 
     return OCEAN_OK;
 }
 
+int ocean_set_spectrum_amplitudes(ocean_generator* gen, int cascade, const float* amplitudes) {
+    OCEAN_ENTER(gen);
+    if (rc) return rc;
+    if ((rc = check_cascade(gen, cascade))) return rc;
+    if (!amplitudes) return fail(OCEAN_ERR_INVALID_ARGUMENT, "amplitudes is NULL");
+    const int N = gen->map_size;
+    std::vector<float> tex((size_t)N * N * 4);
+    for (int y = 0; y < N; ++y)
+        for (int x = 0; x < N; ++x) {
+            const int xm = (N - x) % N, ym = (N - y) % N;                          // ivec2(mod(-id0, dims)), spectrum_compute.glsl:121
+            const float* a0 = amplitudes + ((size_t)y * N + x) * 2;
+            const float* a1 = amplitudes + ((size_t)ym * N + xm) * 2;
+            float* t = tex.data() + ((size_t)y * N + x) * 4;
+            t[0] = a0[0]; t[1] = a0[1]; t[2] = a1[0]; t[3] = -a1[1];                // (h0(k), conj h0(-k))  :124
+        }
+    OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
+    OCEAN_CUDA(cudaMemcpy(gen->buf.spectrum + (size_t)cascade * N * N, tex.data(), sizeof(float) * tex.size(), cudaMemcpyHostToDevice));
+    return OCEAN_OK;
+}
+
 int ocean_enable_f32_taps(ocean_generator* gen, int enable) {
     OCEAN_ENTER(gen);
     if (rc) return rc;

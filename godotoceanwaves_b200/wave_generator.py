@@ -178,6 +178,13 @@ class WaveGenerator:
         check(load_library().ocean_copy_spectrum_to_host(self.context, cascade, out.ctypes.data))
         return out
 
+    def set_spectrum_amplitudes(self, cascade: int, amplitudes) -> None:
+        """Replaces spectrum_compute's output of one cascade by amplitudes [N][N] complex64 (or [N][N][2] float32): A(id) per
+        texel; the library completes the texture with conj A(mod(-id, N)) (spectrum_compute.glsl:121-124)."""
+        self._require()
+        a = np.ascontiguousarray(np.asarray(amplitudes).astype(np.complex64)).view(np.float32).reshape(self.map_size, self.map_size, 2)
+        check(load_library().ocean_set_spectrum_amplitudes(self.context, cascade, a.ctypes.data))
+
     def enable_f32_taps(self, enable: bool = True) -> None:
         self._require()
         check(load_library().ocean_enable_f32_taps(self.context, 1 if enable else 0))

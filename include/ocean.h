@@ -154,6 +154,13 @@ int ocean_host_free(void* ptr);
  * [map_size][map_size][4] float = (Re h0(k), Im h0(k), Re h0(-k), -Im h0(-k)) for one cascade. */
 int ocean_copy_spectrum_to_host(ocean_generator* gen, int cascade, float* host);
 
+/* Injects wave amplitudes in place of spectrum_compute's output (test / authoring tap): amplitudes = [map_size][map_size][2]
+ * float, A(id) for every texel id = (x, y) (the value get_spectrum_amplitude(id) would return, spectrum_compute.glsl:103-115).
+ * The library stores spectrum[id] = (A(id), conj A(mod(-id, N))) exactly as spectrum_compute.glsl:121-124 does, so the texture stays
+ * consistent with what the time-propagation stage assumes.  Pass should_generate_spectrum = 0 for that cascade afterwards, or the
+ * next update regenerates the spectrum from the parameters. */
+int ocean_set_spectrum_amplitudes(ocean_generator* gen, int cascade, const float* amplitudes);
+
 /* Host evaluation of the DETMATH exp: the library computes exp(-foam_decay_rate), uniform per dispatch
  * (fft_unpack.glsl:62), on the host with the same binary64 operation sequence the device functions use.  Exported so
  * that the agreement can be checked without a GPU (tests/test_abi_cpu.py). */

@@ -315,6 +315,12 @@ def test_multi_gpu_sharded_equals_single_gpu():
            "--master-port", "29541", os.path.join(root, "tests", "_sharding_gpu_worker.py")]
     res = subprocess.run(cmd, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                          text=True, timeout=600)
+    try:                                          # keep the workers' output where gpurun brings it back
+        os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(root, "gpurun_out", "sharding_gpu_worker.log"), "w") as f:
+            f.write(res.stdout)
+    except OSError:
+        pass
     assert res.returncode == 0 and "SHARDING_GPU_OK" in res.stdout, res.stdout[-3000:]
 
 
@@ -356,4 +362,40 @@ def test_more_cascades_than_one_launch_holds():
     for k, c in enumerate(pick):
         assert _bits_equal(d16[c].view(np.uint16), o.displacement_map[k]), c
         assert _bits_equal(n16[c].view(np.uint16), o.normal_map[k]), c
+    g.free()
+
+
+def test_wind_fetch_sweep_as_one_batch():
+    """BASELINE.json configs[4]: wind/fetch sweep U = 5..30 m/s x F = 1..1000 km at 256x256 x 4.  The 6 x 4 grid points are
+    24 independent cascade sets of ONE generator: every spectrum of the sweep is generated by one batched spectrum launch
+    (spectrum_compute.glsl:103-125 once per amplitude) and one update produces all maps.  Every spectrum of every grid
+    point is compared with the oracle bit for bit; so are the maps of the two extreme grid points."""
+    import ctypes as C
+    gow = _gpu()
+    N, per_set = 256, 4
+    grid = [(u, f) for u in (5.0, 10.0, 15.0, 20.0, 25.0, 30.0) for f in (1.0, 10.0, 100.0, 1000.0)]
+    total = len(grid) * per_set
+    pg, pcpu = [], []
+    for s, (u, f) in enumerate(grid):
+        for c in range(per_set):
+            over = dict(wind_speed=u, fetch_length=f)
+            pg.append(demo_params(gow.WaveCascadeParameters, s * per_set + c, **over))
+            pcpu.append(demo_params(po.CascadeParams, s * per_set + c, **over))
+    g = gow.WaveGenerator(); g.map_size = N; g.init_gpu(total)
+    launches0 = g.info().kernel_launches
+    g.update_all(0.02, pg)
+    assert g.info().kernel_launches - launches0 == 3          # one spectrum launch, one table launch, one update launch
+    L = po.lib()
+    ref = np.zeros((N, N, 4), np.float32)
+    for i in range(total):
+        pc = po.pc_spectrum_compute(pcpu[i], 0)
+        L.oracle_spectrum_compute(ref.ctypes.data_as(C.POINTER(C.c_float)), N, C.byref(pc))
+        assert _bits_equal(g.spectrum_to_host(i), ref), (i, grid[i // per_set])
+    d16, n16 = g.maps_to_host(0, total)
+    for s in (0, len(grid) - 1):
+        o = po.OracleWaveGenerator(N)
+        o.keep_f32 = False
+        o.update_all(0.02, pcpu[s * per_set:(s + 1) * per_set])
+        assert _bits_equal(d16[s * per_set:(s + 1) * per_set].view(np.uint16), o.displacement_map[:per_set]), grid[s]
+        assert _bits_equal(n16[s * per_set:(s + 1) * per_set].view(np.uint16), o.normal_map[:per_set]), grid[s]
     g.free()
