@@ -212,6 +212,8 @@ def run_reference(args, rank: int):
     if rank != 0:
         return
     C = args.sets * args.cascades_per_set
+    # exactly --steps timed steps after --warmup (>= 3) untimed ones, each step the GPU arm's whole per-GPU workload; the time
+    # budget only guards against a host far slower than expected (the line then reports the steps it did time)
     cb = cpu_arm(args.map_size, C, args.steps, args.warmup, budget_s=args.reference_seconds)
     cps = cb["value"]
     line = {
@@ -290,7 +292,7 @@ def main():
     ap.add_argument("--cascades-per-set", type=int, default=4)
     ap.add_argument("--sets", type=int, default=32, help="independent cascade sets resident per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU-baseline sample budget inside the native arm")
-    ap.add_argument("--reference-seconds", type=float, default=150.0, help="time budget of the whole --impl reference run")
+    ap.add_argument("--reference-seconds", type=float, default=240.0, help="time budget of the whole --impl reference run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4-strong"],
                     help="cfg2: BASELINE configs[1], weak scaling (default, the driver's contract); cfg4-strong: BASELINE configs[3], "

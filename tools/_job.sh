@@ -1,2 +1,2 @@
-timeout 600 python -m pytest tests -m gpu -q --tb=short -x 2>&1 | tail -8
-tools/ab_bench.sh godotoceanwaves_b200/libocean_prev.so godotoceanwaves_b200/libocean.so godotoceanwaves_b200/libocean_keepb.so godotoceanwaves_b200/libocean.so godotoceanwaves_b200/libocean_keepb.so
+timeout 600 python -m pytest tests -m gpu -q --tb=short -x 2>&1 | tail -5
+timeout 600 python tools/run_configs.py 2>&1 | grep -E "cfg5|spectrum generation" | cut -c1-330
