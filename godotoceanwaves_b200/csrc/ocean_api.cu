@@ -333,10 +333,10 @@ int run_cascades(ocean_generator* g, const int* indices, int n) {
             const int m = (n - first < ocean::kMaxPersistentCascades) ? n - first : ocean::kMaxPersistentCascades;
             auto it = g->item_tables.find(m);
             if (it == g->item_tables.end()) {
-                const int group = ocean::persistent_group(g->map_size);
-                const int total = ocean::build_item_table(g->map_size, m, group, nullptr);
+                const int group = ocean::persistent_group(g->map_size), lag = ocean::persistent_lag(g->map_size);
+                const int total = ocean::build_item_table(g->map_size, m, group, lag, nullptr);
                 std::vector<int> host((size_t)total);
-                ocean::build_item_table(g->map_size, m, group, host.data());
+                ocean::build_item_table(g->map_size, m, group, lag, host.data());
                 int* dev = nullptr;
                 RUN_CUDA(dev_alloc(g, &dev, (size_t)total));
                 cudaError_t ce = cudaMemcpyAsync(dev, host.data(), sizeof(int) * (size_t)total, cudaMemcpyHostToDevice, g->stream);
@@ -875,6 +875,20 @@ int ocean_copy_rowpass_to_host(ocean_generator* gen, int cascade, float* host) {
 }
 
 float ocean_detmath_expf(float x) { return exp_det_host(x); }
+
+int ocean_debug_work_queue(int map_size, int count, int group, int lag, int32_t* items, int capacity) {
+    if (ocean::a_items_per_cascade(map_size) == 0 || count < 1 || count > 0x7fff || (items == nullptr && capacity > 0))
+        return -fail(OCEAN_ERR_INVALID_ARGUMENT, "ocean_debug_work_queue: map_size must be 128/256/512/1024, 1 <= count <= 32767");
+    if (group <= 0) group = ocean::persistent_group(map_size);
+    if (lag <= 0) lag = ocean::persistent_lag(map_size);
+    const int total = ocean::build_item_table(map_size, count, group, lag, nullptr);
+    if (items && capacity > 0) {
+        std::vector<int> all((size_t)total);
+        ocean::build_item_table(map_size, count, group, lag, all.data());
+        for (int i = 0; i < total && i < capacity; ++i) items[i] = all[(size_t)i];
+    }
+    return total;
+}
 
 // ---- map queries ----
 namespace {

@@ -89,12 +89,13 @@ constexpr int kMaxPersistentCascades = 256;
 cudaError_t launch_cascade_update_persistent(const DeviceBuffers& b, const CascadeDispatch* dispatch_host, int count,
                                              cudaStream_t stream, int* queue_dev, const int* item_table_dev, int total_items,
                                              int resident_ctas, bool multi_frame = false);
-int build_item_table(int map_size, int count, int group, int* out);
+int build_item_table(int map_size, int count, int group, int lag, int* out);
 // Queue order of `frames` consecutive updates of the same `count` cascades in one launch: per frame A(f, c0..) then B(f, c0..);
 // slot of (frame f, cascade position c) = f * count + c.  A(f+1, c) waits for B(f, c) (CascadeDispatch::wait_target).
 int build_item_table_frames(int map_size, int count, int frames, int* out);
 int b_items_per_cascade(int map_size);
 int persistent_group(int map_size);
+int persistent_lag(int map_size);     // groups between the row pass and the column pass of a group in the queue order
 cudaError_t persistent_grid_size(int map_size, int* out);
 int a_items_per_cascade(int map_size);
 

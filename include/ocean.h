@@ -243,6 +243,13 @@ int ocean_get_last_kernel_times(ocean_generator* gen, float* spectrum_ms, float*
  * (every binary32 in [2^-100, 2^100] for sqrt, ~1.2e9 random pairs for div). */
 int ocean_selftest_math(ocean_generator* gen, uint64_t* failures, uint64_t* tested);
 
+/* Host-side view of the persistent kernel's work queue for `count` cascades of `map_size` (no GPU needed): writes up to `capacity`
+ * packed items (bit 31 = column-pass item, bits 16..30 = cascade position, bits 0..15 = block) in hand-out order for the given
+ * group size and lag (0 = the library's defaults for that map size, after OCEAN_QUEUE_GROUP / OCEAN_QUEUE_LAG) and returns the
+ * item count (negative status on error).  Lets the deadlock-freedom invariant -- every row-pass item of a cascade precedes every
+ * column-pass item of that cascade, each item exactly once -- be checked on the CPU (tests/test_abi_cpu.py). */
+int ocean_debug_work_queue(int map_size, int count, int group, int lag, int32_t* items, int capacity);
+
 int ocean_get_info(ocean_generator* gen, ocean_info* out);
 const char* ocean_last_error(void);
 const char* ocean_version(void);

@@ -119,3 +119,40 @@ def test_host_detmath_exp_matches_the_oracle_bit_for_bit():
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     n = lib.ocean_detmath_expf(float("nan"))
     assert n != n
+
+
+@pytest.mark.parametrize("map_size,count,group,lag", [(256, 128, 0, 0), (256, 128, 16, 1), (256, 7, 2, 3), (128, 9, 3, 4), (512, 16, 0, 0),
+                                                     (1024, 8, 0, 0), (256, 5, 8, 1), (128, 260 % 256 + 4, 1, 1)])
+def test_work_queue_order_is_deadlock_free(map_size, count, group, lag):
+    """The persistent kernel hands work items out in table order and a column-pass (B) item waits for the row pass of its cascade:
+    progress is guaranteed because every row-pass (A) item of a cascade precedes every B item of that cascade (a waiting team only
+    waits for items that were handed out before its own).  Checked on the host for the default shapes and for shapes with more lag
+    than groups: each item exactly once, A before B per cascade, and never more than (lag + 1) groups between the two passes."""
+    import ctypes as C
+    lib = native.load_library()
+    total = lib.ocean_debug_work_queue(map_size, count, group, lag, None, 0)
+    assert total > 0
+    items = (C.c_int32 * total)()
+    assert lib.ocean_debug_work_queue(map_size, count, group, lag, items, total) == total
+    codes = np.frombuffer(items, dtype=np.int32).astype(np.int64) & 0xFFFFFFFF
+    is_b = (codes >> 31) & 1
+    slot = (codes >> 16) & 0x7FFF
+    block = codes & 0xFFFF
+    assert slot.max() == count - 1
+    seen = set()
+    last_a = {}
+    first_b = {}
+    for pos, (b, s, x) in enumerate(zip(is_b, slot, block)):
+        key = (int(b), int(s), int(x))
+        assert key not in seen
+        seen.add(key)
+        if b:
+            first_b.setdefault(int(s), pos)
+        else:
+            last_a[int(s)] = pos
+    a_per = sum(1 for k in seen if k[0] == 0 and k[1] == 0)
+    b_per = sum(1 for k in seen if k[0] == 1 and k[1] == 0)
+    assert len(seen) == count * (a_per + b_per) and a_per > 0 and b_per > 0
+    for s in range(count):
+        assert last_a[s] < first_b[s], s
+    assert is_b[0] == 0 and is_b[-1] == 1

@@ -324,13 +324,15 @@ def test_multi_gpu_sharded_equals_single_gpu():
     assert res.returncode == 0 and "SHARDING_GPU_OK" in res.stdout, res.stdout[-3000:]
 
 
-@pytest.mark.parametrize("group", ["1", "2"])
-def test_interleaved_queue_groups_against_oracle(group, monkeypatch):
-    """The persistent kernel's work queue runs A(g+1) items between A(g) and B(g): with one or two cascades per group and
-    seven cascades every hand-over of the landing buffer (A -> B, B -> B with a pre-issued panel, B -> A) occurs; all
-    textures must still equal the oracle's bit for bit over three updates."""
+@pytest.mark.parametrize("group,lag", [("1", "1"), ("2", "1"), ("1", "3"), ("2", "2"), ("3", "4")])
+def test_interleaved_queue_groups_against_oracle(group, lag, monkeypatch):
+    """The persistent kernel's work queue runs the row-pass items of the next `lag` groups between A(g) and B(g): with one to three
+    cascades per group and seven cascades every hand-over of the landing buffer (A -> B, B -> B with a pre-issued panel, B -> A)
+    and both ends of the order (lag larger than the number of groups included) occur; all textures must still equal the oracle's
+    bit for bit over three updates."""
     gow = _gpu()
     monkeypatch.setenv("OCEAN_QUEUE_GROUP", group)
+    monkeypatch.setenv("OCEAN_QUEUE_LAG", lag)
     N, C = 128, 7
     pg, pcpu = _pair(gow.WaveCascadeParameters, C)
     g = gow.WaveGenerator(); g.map_size = N; g.init_gpu(C)
