@@ -77,6 +77,7 @@ struct ocean_generator {
     std::vector<char> slot_valid;
     std::vector<int> slot_refs;                         // cascades currently pointing at the slot
     std::vector<int> cascade_slot;                      // [num_cascades] slot of each cascade, -1 = none yet
+    std::vector<int> scratch_layer_of;                  // [num_cascades] where the last update left the cascade's row pass (debug tap)
     cudaEvent_t ring_done[kRing] = {};
     int ring_next = 0;
     cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
@@ -84,7 +85,7 @@ struct ocean_generator {
     int prof_chunk = 0;                                 // cascades in the profiled first chunk
     bool profiling = false;
     bool prof_valid = false, prof_had_gen = false;
-    int* d_queue = nullptr;                             // [1 + num_cascades] work counter + completion counters
+    int* d_queue = nullptr;                             // [1 + 3 * num_cascades] work counter + completion counters
     std::vector<uint32_t> done_count;                   // host mirror of the completion counters (modulo 2^32)
     int resident_ctas = 0;
     std::map<int, std::pair<int*, int>> item_tables;    // cascades per launch -> (device item table, item count)
@@ -236,6 +237,9 @@ ocean::CascadeDispatch make_cascade_dispatch(const ocean_cascade_params& p, int 
     d.foam_decay_factor = exp_det_host(-(float)p.foam_decay_rate);
     d.done_target = 0;
     d.wait_target = 0;
+    d.col_wait_target = 0;
+    d.done_slot = cascade;
+    d.scratch_layer = 2 * cascade;                    // half 0 of the scratch (single updates always use it)
     return d;
 }
 
@@ -294,6 +298,7 @@ int run_cascades(ocean_generator* g, const int* indices, int n) {
         if (ts < 0) return fail(OCEAN_ERR_STATE, "no free dispersion-table slot (internal error)");
         hc[k] = make_cascade_dispatch(p, i, ts);                     // :73,85
         hc[k].done_target = g->done_count[i] + per_update;           // modulo 2^32
+        g->scratch_layer_of[i] = hc[k].scratch_layer;
     }
     // From here on the device is touched.  The host-side state that must agree with it (dirty flags, the mirror of
     // the completion counters, the staging ring) is committed only after everything has been enqueued; on a failure
@@ -467,7 +472,7 @@ int ocean_create(int device, int map_size, int num_cascades, ocean_generator** o
     } while (0)
     CREATE_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     CREATE_CUDA(dev_alloc(g, &g->buf.spectrum, C * NN));                  // wave_generator.gd:31
-    CREATE_CUDA(dev_alloc(g, &g->buf.rowpass, C * 2 * NN));               // replaces fft_buffer, :33
+    CREATE_CUDA(dev_alloc(g, &g->buf.rowpass, ocean::kScratchHalves * C * 2 * NN));               // replaces fft_buffer, :33
     CREATE_CUDA(dev_alloc(g, &g->buf.displacement, C * NN));              // :34
     CREATE_CUDA(dev_alloc(g, &g->buf.normal, C * NN));                    // :35
     CREATE_CUDA(dev_alloc(g, &g->twiddles, (size_t)ocean::kTwiddleCount + 1));   // :32
@@ -476,13 +481,15 @@ int ocean_create(int device, int map_size, int num_cascades, ocean_generator** o
     CREATE_CUDA(dev_alloc(g, &g->d_cascade, C));
     CREATE_CUDA(dev_alloc(g, &g->d_spectrum, C));
     CREATE_CUDA(dev_alloc(g, &g->d_tables, C));
-    CREATE_CUDA(dev_alloc(g, &g->d_queue, 2 * C + 1));
-    CREATE_CUDA(cudaMemsetAsync(g->d_queue, 0, sizeof(int) * (2 * C + 1), g->stream));
-    g->done_count.assign(2 * C, 0u);                  // [0, C): row-pass counters, [C, 2C): column-pass counters
+    CREATE_CUDA(dev_alloc(g, &g->d_queue, 3 * C + 1));
+    CREATE_CUDA(cudaMemsetAsync(g->d_queue, 0, sizeof(int) * (3 * C + 1), g->stream));
+    g->done_count.assign(3 * C, 0u);                  // [0, C): row-pass counters (scratch half 0), [C, 2C): column pass, [2C, 3C): row pass, half 1
     g->slot_key.assign(C, ocean_generator::TableKey{0.f, 0.f, 0.f});
     g->slot_valid.assign(C, 0);
     g->slot_refs.assign(C, 0);
     g->cascade_slot.assign(C, -1);
+    g->scratch_layer_of.resize(C);
+    for (int i = 0; i < C; ++i) g->scratch_layer_of[i] = 2 * i;
     {
         const char* mode = std::getenv("OCEAN_PIPELINE");
         g->persistent = !(mode && std::strcmp(mode, "split") == 0);
@@ -496,7 +503,7 @@ int ocean_create(int device, int map_size, int num_cascades, ocean_generator** o
     for (auto& ev : g->prof) CREATE_CUDA(cudaEventCreate(&ev));
     // textures start cleared (foam state = 0)
     CREATE_CUDA(cudaMemsetAsync(g->buf.spectrum, 0, sizeof(float4) * C * NN, g->stream));
-    CREATE_CUDA(cudaMemsetAsync(g->buf.rowpass, 0, sizeof(float4) * C * 2 * NN, g->stream));
+    CREATE_CUDA(cudaMemsetAsync(g->buf.rowpass, 0, sizeof(float4) * ocean::kScratchHalves * C * 2 * NN, g->stream));
     CREATE_CUDA(cudaMemsetAsync(g->buf.displacement, 0, sizeof(uint2) * C * NN, g->stream));
     CREATE_CUDA(cudaMemsetAsync(g->buf.normal, 0, sizeof(uint2) * C * NN, g->stream));
     g->buf.map_size = map_size;
@@ -606,8 +613,17 @@ int ocean_update_frames(ocean_generator* gen, double delta, ocean_cascade_params
                 p.foam_grow_rate = delta * p.foam_amount * 7.5;
                 p.foam_decay_rate = delta * std::fmax(0.5, 10.0 - p.foam_amount) * 1.15;
                 ocean::CascadeDispatch d = make_cascade_dispatch(p, i, gen->cascade_slot[i]);
-                d.done_target = gen->done_count[i] + (uint32_t)(f + 1) * a_per;
-                d.wait_target = gen->done_count[C + i] + (uint32_t)f * b_per;
+                // Frame `done + f` of this call runs in half (done + f) & 1 of the scratch, so the row pass of a frame only waits for
+                // the column pass two frames back (every frame of earlier launches is complete when this launch starts) and runs
+                // beside the previous frame's column pass; the column pass waits for its own row pass and -- foam plane, maps -- for
+                // the previous frame's column pass.
+                const int half = (done + f) & 1;
+                d.done_slot = half ? 2 * C + i : i;                         // the halves count their row passes separately:
+                d.done_target = gen->done_count[d.done_slot] + (uint32_t)(f / 2 + 1) * a_per;   // frames f, f-2, ... of this launch
+                d.wait_target = gen->done_count[C + i] + (uint32_t)(f > 0 ? f - 1 : 0) * b_per;
+                d.col_wait_target = gen->done_count[C + i] + (uint32_t)f * b_per;
+                d.scratch_layer = 2 * (half * C + i);
+                gen->scratch_layer_of[i] = d.scratch_layer;
                 rec[(size_t)f * count + i] = d;
             }
         }
@@ -635,7 +651,9 @@ int ocean_update_frames(ocean_generator* gen, double delta, ocean_cascade_params
             return fail(OCEAN_ERR_CUDA, "multi-frame launch failed: %s", cudaGetErrorString(le));
         }
         for (int i = 0; i < count; ++i) {
-            gen->done_count[i] += (uint32_t)F * a_per;
+            const int first_half = done & 1;                               // half of the launch's frame 0; it runs (F + 1) / 2 frames there
+            gen->done_count[first_half ? 2 * C + i : i] += (uint32_t)((F + 1) / 2) * a_per;
+            gen->done_count[first_half ? i : 2 * C + i] += (uint32_t)(F / 2) * a_per;
             gen->done_count[C + i] += (uint32_t)F * b_per;
         }
         gen->kernel_launches += 1;
@@ -867,7 +885,7 @@ int ocean_copy_rowpass_to_host(ocean_generator* gen, int cascade, float* host) {
     if (!gen->buf.displacement_f32) return fail(OCEAN_ERR_STATE, "the row-pass scratch is only kept while the taps are on; call ocean_enable_f32_taps(gen, 1) before the update");
     const size_t layer = (size_t)gen->map_size * gen->map_size;
     if (!gen->export_buf) OCEAN_CUDA(dev_alloc(gen, &gen->export_buf, 4 * layer));
-    OCEAN_CUDA(ocean::launch_rowpass_export(gen->buf, cascade, gen->export_buf, gen->stream));
+    OCEAN_CUDA(ocean::launch_rowpass_export(gen->buf, gen->scratch_layer_of[cascade], gen->export_buf, gen->stream));
     gen->kernel_launches += 1;
     OCEAN_CUDA(cudaMemcpyAsync(host, gen->export_buf, sizeof(float2) * 4 * layer, cudaMemcpyDeviceToHost, gen->stream));
     OCEAN_CUDA(cudaStreamSynchronize(gen->stream));
@@ -876,15 +894,19 @@ int ocean_copy_rowpass_to_host(ocean_generator* gen, int cascade, float* host) {
 
 float ocean_detmath_expf(float x) { return exp_det_host(x); }
 
-int ocean_debug_work_queue(int map_size, int count, int group, int lag, int32_t* items, int capacity) {
-    if (ocean::a_items_per_cascade(map_size) == 0 || count < 1 || count > 0x7fff || (items == nullptr && capacity > 0))
-        return -fail(OCEAN_ERR_INVALID_ARGUMENT, "ocean_debug_work_queue: map_size must be 128/256/512/1024, 1 <= count <= 32767");
+int ocean_debug_work_queue(int map_size, int count, int group, int lag, int frames, int32_t* items, int capacity) {
+    if (ocean::a_items_per_cascade(map_size) == 0 || count < 1 || frames < 0 || (long long)count * (frames > 0 ? frames : 1) > 0x7fff ||
+        (items == nullptr && capacity > 0))
+        return -fail(OCEAN_ERR_INVALID_ARGUMENT, "ocean_debug_work_queue: map_size must be 128/256/512/1024, 1 <= count * frames <= 32767");
     if (group <= 0) group = ocean::persistent_group(map_size);
     if (lag <= 0) lag = ocean::persistent_lag(map_size);
-    const int total = ocean::build_item_table(map_size, count, group, lag, nullptr);
+    auto build = [&](int* out) {
+        return frames > 0 ? ocean::build_item_table_frames(map_size, count, frames, out) : ocean::build_item_table(map_size, count, group, lag, out);
+    };
+    const int total = build(nullptr);
     if (items && capacity > 0) {
         std::vector<int> all((size_t)total);
-        ocean::build_item_table(map_size, count, group, lag, all.data());
+        build(all.data());
         for (int i = 0; i < total && i < capacity; ++i) items[i] = all[(size_t)i];
     }
     return total;

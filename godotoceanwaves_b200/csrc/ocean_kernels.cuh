@@ -26,10 +26,18 @@ struct CascadeDispatch {
     int32_t table_slot;
     float time;
     float whitecap, foam_grow_rate, foam_decay_factor;   // factor = DETMATH exp(-foam_decay_rate), fft_unpack.glsl:62 (uniform per dispatch)
-    uint32_t done_target;  // persistent kernel: value of done[cascade] once this update's row pass is complete (wraps)
-    uint32_t wait_target;  // multi-frame launches: value of colpass_done[cascade] once the PREVIOUS frame's column pass of this
-                           // cascade is complete -- its row pass may then overwrite the scratch (0-frame lag: == current value)
+    uint32_t done_target;  // persistent kernel: value of done[done_slot] once this update's row pass is complete (wraps)
+    uint32_t wait_target;  // multi-frame launches: value of colpass_done[cascade] once the column pass that last READ this update's
+                           // half of the scratch (two frames back) is complete -- the row pass may then overwrite it
+    uint32_t col_wait_target;  // multi-frame launches: value of colpass_done[cascade] once the PREVIOUS frame's column pass is complete
+                               // (it owns the foam plane this update's column pass reads and the maps it overwrites)
+    int32_t done_slot;     // row-pass completion counter of this update: cascade (scratch half 0) or 2 * num_cascades + cascade
+                           // (half 1) -- one counter per half, because the row pass of frame f+1 runs beside the column pass
+                           // of frame f and its items must not be counted towards frame f's row pass
+    int32_t scratch_layer; // first of the cascade's two layer pairs in the row-pass scratch: 2 * cascade in half 0,
+                           // 2 * (num_cascades + cascade) in half 1 (consecutive frames of a multi-frame launch alternate)
 };
+constexpr int kScratchHalves = 2;
 
 // One dispersion table to (re)build: spectrum_modulate.glsl:59-61,49 for every wave vector of a tile.
 struct TableDispatch {
@@ -41,7 +49,7 @@ struct DeviceBuffers {
     int map_size;
     int num_cascades;
     float4* spectrum;      // [C][N][N] (Re h0(k), Im h0(k), Re h0(-k), -Im h0(-k))      RGBA32F
-    float4* rowpass;       // [C][2][N][N] (re_a, re_b, im_a, im_b), pair p = layers (2p, 2p+1)
+    float4* rowpass;       // [kScratchHalves][C][2][N][N] (re_a, re_b, im_a, im_b), pair p = layers (2p, 2p+1)
     uint2* displacement;   // [C][N][N] 4 x half                                          RGBA16F
     uint2* normal;         // [C][N][N] 4 x half, .a = foam state                         RGBA16F
     float4* displacement_f32;  // optional taps (nullptr when disabled)
@@ -80,8 +88,9 @@ int chunk_cascades(int map_size);
 
 // Same work as launch_cascade_update in ONE persistent launch (work queue over A and B items, B items
 // wait on per-cascade completion counters).  `dispatch_host` (<= kMaxPersistentCascades records) travels by
-// value as a kernel parameter (constant bank).  queue_dev: [0] = work counter, [1 + c] = completion counter of
-// cascade c (monotonic; dispatch[i].done_target is the value to wait for).  item_table_dev/total_items from
+// value as a kernel parameter (constant bank).  queue_dev: [0] = work counter, [1 + s] = completion counter s (row pass of
+// cascade c in scratch half 0: s = c, column pass: C + c, row pass in half 1: 2C + c; monotonic modulo 2^32;
+// dispatch[i].done_target is the value of counter done_slot to wait for).  item_table_dev/total_items from
 // build_item_table(map_size, count, persistent_group(map_size)); resident_ctas from persistent_grid_size().
 constexpr int kMaxPersistentCascades = 256;
 // multi_frame: the records describe several consecutive updates of the same cascades (build_item_table_frames): B items then
@@ -90,8 +99,9 @@ cudaError_t launch_cascade_update_persistent(const DeviceBuffers& b, const Casca
                                              cudaStream_t stream, int* queue_dev, const int* item_table_dev, int total_items,
                                              int resident_ctas, bool multi_frame = false);
 int build_item_table(int map_size, int count, int group, int lag, int* out);
-// Queue order of `frames` consecutive updates of the same `count` cascades in one launch: per frame A(f, c0..) then B(f, c0..);
-// slot of (frame f, cascade position c) = f * count + c.  A(f+1, c) waits for B(f, c) (CascadeDispatch::wait_target).
+// Queue order of `frames` consecutive updates of the same `count` cascades in one launch: A(f0) A(f1) B(f0) A(f2) B(f1) ... with
+// A(f) = the row-pass items of every cascade; slot of (frame f, cascade position c) = f * count + c.  Frames alternate between the
+// halves of the scratch: A(f, c) waits for B(f-2, c) (CascadeDispatch::wait_target), B(f, c) for A(f, c) and B(f-1, c).
 int build_item_table_frames(int map_size, int count, int frames, int* out);
 int b_items_per_cascade(int map_size);
 int persistent_group(int map_size);
@@ -103,7 +113,7 @@ int a_items_per_cascade(int map_size);
 cudaError_t launch_selftest_math(unsigned long long* failures_dev, unsigned long long* tested_dev, cudaStream_t stream);
 
 // De-interleaves one cascade of the row-pass scratch into [4][N][N][2] floats (debug tap).
-cudaError_t launch_rowpass_export(const DeviceBuffers& b, int cascade, float2* out_dev, cudaStream_t stream);
+cudaError_t launch_rowpass_export(const DeviceBuffers& b, int scratch_layer, float2* out_dev, cudaStream_t stream);
 // ocean_sample.cu: batched map queries (water.gdshader:27-39,42-84); scales_dev = map_scales[num_cascades] as float4
 cudaError_t launch_sample_maps(const DeviceBuffers& b, int num_cascades, const float2* points_dev, int n, const float4* scales_dev,
                                float* disp_out_dev, float* grad_out_dev, cudaStream_t stream);

@@ -100,9 +100,10 @@ int ocean_process(ocean_generator* gen, ocean_cascade_params* parameters, int co
 int ocean_update_all(ocean_generator* gen, double delta, ocean_cascade_params* parameters, int count);
 
 /* `frames` consecutive ocean_update_all(delta) calls of the same resident cascades, fused: after the first frame the
- * remaining ones run `256 / count` frames per launch, chained on the device through per-cascade completion counters (the row
- * pass of frame f+1 waits for the column pass of frame f of the same cascade; the times are accumulated on the host in
- * binary64, one addition per frame, exactly as wave_generator.gd:103 does).  Results are bit-identical to the frame-by-frame
+ * remaining ones run `256 / count` frames per launch, chained on the device through per-cascade completion counters (consecutive
+ * frames use alternate halves of the row-pass scratch: the row pass of frame f+1 runs beside the column pass of frame f and only
+ * waits for the column pass of frame f-1, the column pass of frame f+1 for its own row pass and -- foam plane -- for the column
+ * pass of frame f; the times are accumulated on the host in binary64, one addition per frame, exactly as wave_generator.gd:103 does).  Results are bit-identical to the frame-by-frame
  * calls; what it removes is the per-frame launch and host latency (1000-frame foam accumulate/decay loop). */
 int ocean_update_frames(ocean_generator* gen, double delta, ocean_cascade_params* parameters, int count, int frames);
 
@@ -244,11 +245,13 @@ int ocean_get_last_kernel_times(ocean_generator* gen, float* spectrum_ms, float*
 int ocean_selftest_math(ocean_generator* gen, uint64_t* failures, uint64_t* tested);
 
 /* Host-side view of the persistent kernel's work queue for `count` cascades of `map_size` (no GPU needed): writes up to `capacity`
- * packed items (bit 31 = column-pass item, bits 16..30 = cascade position, bits 0..15 = block) in hand-out order for the given
- * group size and lag (0 = the library's defaults for that map size, after OCEAN_QUEUE_GROUP / OCEAN_QUEUE_LAG) and returns the
- * item count (negative status on error).  Lets the deadlock-freedom invariant -- every row-pass item of a cascade precedes every
- * column-pass item of that cascade, each item exactly once -- be checked on the CPU (tests/test_abi_cpu.py). */
-int ocean_debug_work_queue(int map_size, int count, int group, int lag, int32_t* items, int capacity);
+ * packed items (bit 31 = column-pass item, bits 16..30 = dispatch slot, bits 0..15 = block) in hand-out order and returns the item
+ * count (negative status on error).  frames == 0: the order of a single update for the given group size and lag (0 = the library's
+ * defaults for that map size, after OCEAN_QUEUE_GROUP / OCEAN_QUEUE_LAG), slot = cascade position.  frames >= 1: the order of a
+ * fused launch of that many consecutive updates (ocean_update_frames), slot = frame * count + cascade position.  Lets the
+ * deadlock-freedom invariant -- whatever an item waits for was handed out before it, each item exactly once -- be checked on the
+ * CPU (tests/test_abi_cpu.py). */
+int ocean_debug_work_queue(int map_size, int count, int group, int lag, int frames, int32_t* items, int capacity);
 
 int ocean_get_info(ocean_generator* gen, ocean_info* out);
 const char* ocean_last_error(void);

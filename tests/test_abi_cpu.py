@@ -130,10 +130,10 @@ def test_work_queue_order_is_deadlock_free(map_size, count, group, lag):
     than groups: each item exactly once, A before B per cascade, and never more than (lag + 1) groups between the two passes."""
     import ctypes as C
     lib = native.load_library()
-    total = lib.ocean_debug_work_queue(map_size, count, group, lag, None, 0)
+    total = lib.ocean_debug_work_queue(map_size, count, group, lag, 0, None, 0)
     assert total > 0
     items = (C.c_int32 * total)()
-    assert lib.ocean_debug_work_queue(map_size, count, group, lag, items, total) == total
+    assert lib.ocean_debug_work_queue(map_size, count, group, lag, 0, items, total) == total
     codes = np.frombuffer(items, dtype=np.int32).astype(np.int64) & 0xFFFFFFFF
     is_b = (codes >> 31) & 1
     slot = (codes >> 16) & 0x7FFF
@@ -156,3 +156,39 @@ def test_work_queue_order_is_deadlock_free(map_size, count, group, lag):
     for s in range(count):
         assert last_a[s] < first_b[s], s
     assert is_b[0] == 0 and is_b[-1] == 1
+
+
+@pytest.mark.parametrize("map_size,count,frames", [(512, 4, 64), (256, 4, 3), (128, 1, 1), (256, 7, 2), (1024, 8, 5)])
+def test_fused_frames_queue_order_is_deadlock_free(map_size, count, frames):
+    """ocean_update_frames: frames alternate between the two halves of the row-pass scratch.  A row-pass item of (frame f, cascade c)
+    waits for the column pass of (f - 2, c) -- the last reader of its half --, a column-pass item of (f, c) for the row pass of
+    (f, c) and for the column pass of (f - 1, c) (foam plane, maps).  Every one of those must precede the waiting item in the
+    hand-out order; every item appears exactly once."""
+    import ctypes as C
+    lib = native.load_library()
+    total = lib.ocean_debug_work_queue(map_size, count, 0, 0, frames, None, 0)
+    assert total > 0
+    items = (C.c_int32 * total)()
+    assert lib.ocean_debug_work_queue(map_size, count, 0, 0, frames, items, total) == total
+    codes = np.frombuffer(items, dtype=np.int32).astype(np.int64) & 0xFFFFFFFF
+    is_b, slot, block = (codes >> 31) & 1, (codes >> 16) & 0x7FFF, codes & 0xFFFF
+    first = {}      # (kind, frame, cascade) -> first position
+    last = {}
+    seen = set()
+    for pos, (b, s, x) in enumerate(zip(is_b, slot, block)):
+        key = (int(b), int(s), int(x))
+        assert key not in seen
+        seen.add(key)
+        k = (int(b), int(s) // count, int(s) % count)
+        first.setdefault(k, pos)
+        last[k] = pos
+    assert len(first) == 2 * frames * count
+    per = {0: sum(1 for k in seen if k[0] == 0 and k[1] == 0), 1: sum(1 for k in seen if k[0] == 1 and k[1] == 0)}
+    assert len(seen) == frames * count * (per[0] + per[1])
+    for f in range(frames):
+        for c in range(count):
+            assert last[(0, f, c)] < first[(1, f, c)]
+            if f >= 1:
+                assert last[(1, f - 1, c)] < first[(1, f, c)]
+            if f >= 2:
+                assert last[(1, f - 2, c)] < first[(0, f, c)]
