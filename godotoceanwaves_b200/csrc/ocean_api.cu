@@ -586,6 +586,47 @@ int ocean_update_all(ocean_generator* gen, double delta, ocean_cascade_params* p
     return OCEAN_OK;
 }
 
+// ---- completion-counter protocol of a fused launch: pure host arithmetic, shared by ocean_update_frames and by
+// ocean_debug_frame_protocol (tests/test_queue_protocol_cpu.py runs it against random schedules on the CPU) ----
+// counters[0, C): row passes in scratch half 0, [C, 2C): column passes, [2C, 3C): row passes in half 1 -- their values when the
+// launch starts (every earlier launch is complete by then).  Frame f of the launch is frame first_frame + f of the call.
+// Frame `first_frame + f` runs in half (first_frame + f) & 1 of the scratch, so its row pass only waits for the column pass two
+// frames back and runs beside the previous frame's column pass; its column pass waits for its own row pass and -- foam plane,
+// maps -- for the previous frame's column pass.  The halves count their row passes separately (frames f, f-2, ... of the launch).
+static void frame_protocol_targets(ocean::CascadeDispatch& d, const uint32_t* counters, int C, int i, int first_frame, int f,
+                                   uint32_t a_per, uint32_t b_per) {
+    const int half = (first_frame + f) & 1;
+    d.done_slot = half ? 2 * C + i : i;
+    d.done_target = counters[d.done_slot] + (uint32_t)(f / 2 + 1) * a_per;
+    d.wait_target = counters[C + i] + (uint32_t)(f > 0 ? f - 1 : 0) * b_per;
+    d.col_wait_target = counters[C + i] + (uint32_t)f * b_per;
+    d.scratch_layer = 2 * (half * C + i);
+}
+// the counters once a launch of F frames starting at frame first_frame is complete
+static void frame_protocol_commit(uint32_t* counters, int C, int i, int first_frame, int F, uint32_t a_per, uint32_t b_per) {
+    const int first_half = first_frame & 1;                        // half of the launch's frame 0; it runs (F + 1) / 2 frames there
+    counters[first_half ? 2 * C + i : i] += (uint32_t)((F + 1) / 2) * a_per;
+    counters[first_half ? i : 2 * C + i] += (uint32_t)(F / 2) * a_per;
+    counters[C + i] += (uint32_t)F * b_per;
+}
+
+int ocean_debug_frame_protocol(int map_size, int num_cascades, int count, int first_frame, int frames, uint32_t* counters, int32_t* records) {
+    const uint32_t a_per = (uint32_t)ocean::a_items_per_cascade(map_size), b_per = (uint32_t)ocean::b_items_per_cascade(map_size);
+    if (a_per == 0 || num_cascades < 1 || count < 1 || count > num_cascades || first_frame < 0 || frames < 1 || !counters || !records)
+        return fail(OCEAN_ERR_INVALID_ARGUMENT, "ocean_debug_frame_protocol: bad arguments");
+    for (int f = 0; f < frames; ++f)
+        for (int i = 0; i < count; ++i) {
+            ocean::CascadeDispatch d{};
+            d.cascade = i;
+            frame_protocol_targets(d, counters, num_cascades, i, first_frame, f, a_per, b_per);
+            int32_t* r = records + ((size_t)f * count + i) * 6;
+            r[0] = d.cascade; r[1] = d.done_slot; r[2] = (int32_t)d.done_target; r[3] = (int32_t)d.wait_target;
+            r[4] = (int32_t)d.col_wait_target; r[5] = d.scratch_layer;
+        }
+    for (int i = 0; i < count; ++i) frame_protocol_commit(counters, num_cascades, i, first_frame, frames, a_per, b_per);
+    return OCEAN_OK;
+}
+
 int ocean_update_frames(ocean_generator* gen, double delta, ocean_cascade_params* parameters, int count, int frames) {
     OCEAN_ENTER(gen);
     if (rc) return rc;
@@ -613,16 +654,7 @@ int ocean_update_frames(ocean_generator* gen, double delta, ocean_cascade_params
                 p.foam_grow_rate = delta * p.foam_amount * 7.5;
                 p.foam_decay_rate = delta * std::fmax(0.5, 10.0 - p.foam_amount) * 1.15;
                 ocean::CascadeDispatch d = make_cascade_dispatch(p, i, gen->cascade_slot[i]);
-                // Frame `done + f` of this call runs in half (done + f) & 1 of the scratch, so the row pass of a frame only waits for
-                // the column pass two frames back (every frame of earlier launches is complete when this launch starts) and runs
-                // beside the previous frame's column pass; the column pass waits for its own row pass and -- foam plane, maps -- for
-                // the previous frame's column pass.
-                const int half = (done + f) & 1;
-                d.done_slot = half ? 2 * C + i : i;                         // the halves count their row passes separately:
-                d.done_target = gen->done_count[d.done_slot] + (uint32_t)(f / 2 + 1) * a_per;   // frames f, f-2, ... of this launch
-                d.wait_target = gen->done_count[C + i] + (uint32_t)(f > 0 ? f - 1 : 0) * b_per;
-                d.col_wait_target = gen->done_count[C + i] + (uint32_t)f * b_per;
-                d.scratch_layer = 2 * (half * C + i);
+                frame_protocol_targets(d, gen->done_count.data(), C, i, done, f, a_per, b_per);
                 gen->scratch_layer_of[i] = d.scratch_layer;
                 rec[(size_t)f * count + i] = d;
             }
@@ -650,12 +682,7 @@ int ocean_update_frames(ocean_generator* gen, double delta, ocean_cascade_params
             cudaMemcpy(gen->d_queue + 1, gen->done_count.data(), sizeof(uint32_t) * gen->done_count.size(), cudaMemcpyHostToDevice);
             return fail(OCEAN_ERR_CUDA, "multi-frame launch failed: %s", cudaGetErrorString(le));
         }
-        for (int i = 0; i < count; ++i) {
-            const int first_half = done & 1;                               // half of the launch's frame 0; it runs (F + 1) / 2 frames there
-            gen->done_count[first_half ? 2 * C + i : i] += (uint32_t)((F + 1) / 2) * a_per;
-            gen->done_count[first_half ? i : 2 * C + i] += (uint32_t)(F / 2) * a_per;
-            gen->done_count[C + i] += (uint32_t)F * b_per;
-        }
+        for (int i = 0; i < count; ++i) frame_protocol_commit(gen->done_count.data(), C, i, done, F, a_per, b_per);
         gen->kernel_launches += 1;
         gen->cascade_updates += (uint64_t)F * count;
         done += F;

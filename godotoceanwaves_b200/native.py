@@ -67,6 +67,7 @@ SIGNATURES = {
     "ocean_copy_rowpass_to_host": (C.c_int, [_H, C.c_int, C.c_void_p]),
     "ocean_copy_twiddles_to_host": (C.c_int, [_H, C.c_void_p]),
     "ocean_detmath_expf": (C.c_float, [C.c_float]),
+    "ocean_debug_frame_protocol": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ocean_debug_work_queue": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "ocean_sample_maps": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ocean_sample_maps_device": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

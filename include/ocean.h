@@ -253,6 +253,16 @@ int ocean_selftest_math(ocean_generator* gen, uint64_t* failures, uint64_t* test
  * CPU (tests/test_abi_cpu.py). */
 int ocean_debug_work_queue(int map_size, int count, int group, int lag, int frames, int32_t* items, int capacity);
 
+/* Host-side view of the completion-counter protocol of a fused launch (ocean_update_frames; no GPU needed).  `counters` holds
+ * 3 * num_cascades values -- [c] row passes of cascade c in scratch half 0, [num_cascades + c] its column passes,
+ * [2 * num_cascades + c] its row passes in half 1 -- as they stand when a launch of `frames` frames (frame indices first_frame,
+ * first_frame + 1, ... of the call) over cascades 0..count-1 starts; on return they hold the values after the launch.  `records`
+ * receives, per (frame, cascade) in the dispatch-slot order of ocean_debug_work_queue(frames >= 1), six int32:
+ * cascade, counter the row pass bumps / the column pass waits on, its target, the column-pass count the row pass waits for, the
+ * column-pass count the column pass waits for, first scratch layer pair.  tests/test_queue_protocol_cpu.py runs this protocol on
+ * the CPU against random team schedules and checks that no item ever reads unfinished or overwritten data and that nobody waits forever. */
+int ocean_debug_frame_protocol(int map_size, int num_cascades, int count, int first_frame, int frames, uint32_t* counters, int32_t* records);
+
 int ocean_get_info(ocean_generator* gen, ocean_info* out);
 const char* ocean_last_error(void);
 const char* ocean_version(void);
